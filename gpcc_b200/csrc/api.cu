@@ -1,0 +1,713 @@
+// C ABI of libgpcc_b200.so (include/gpcc_b200.h): contexts, problems, batched evaluation, the
+// host-driven batched L-BFGS fit, the grid posterior, postb and predictions.
+// There is no CPU fallback anywhere in this file: every likelihood value comes from a CUDA kernel.
+#include "../../include/gpcc_b200.h"
+#include "gpcc_internal.h"
+#include "lbfgs.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace gpcc;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            cudaGetLastError();                                                                   \
+            return fail(1000 + (int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+        }                                                                                         \
+    } while (0)
+
+template <class T>
+struct DevBuf {   // growable device buffer + pinned host mirror
+    T* d = nullptr;
+    T* h = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t c = std::max<size_t>(n, 1024);
+        c = c + c / 2;
+        cudaError_t e = cudaMalloc(&d, c * sizeof(T));
+        if (e != cudaSuccess) return e;
+        e = cudaMallocHost(&h, c * sizeof(T));
+        if (e != cudaSuccess) return e;
+        cap = c;
+        return cudaSuccess;
+    }
+    void release() {
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        d = nullptr; h = nullptr; cap = 0;
+    }
+};
+
+struct DeviceState {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<double> delays, alpha, rho, ll, grad;
+    DevBuf<int> info;
+    LargeWorkspace large;     // tiled large-N path (large_path.cu)
+    // per-call statistics (profiling)
+    double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
+    long long launches = 0, evals = 0, evals_grad = 0;
+    std::string err;
+    int err_code = 0;
+};
+
+}  // namespace
+
+struct gpcc_ctx {
+    std::vector<DeviceState> ds;
+    bool profiling = false;
+    gpcc_stats stats{};
+    NcclBridge* nccl = nullptr;
+};
+
+struct gpcc_problem {
+    gpcc_ctx* ctx = nullptr;
+    int L = 0, N = 0, kernel_id = 0;
+    std::vector<int> n_per_band, band, band_start;
+    std::vector<double> t, y, sigma, mub, Sigmab, resid, s2, sigb;
+    struct PerDev {
+        double *t = nullptr, *resid = nullptr, *s2 = nullptr, *sigb = nullptr;
+        int* band = nullptr;
+        DevProblem dp;
+    };
+    std::vector<PerDev> pd;
+    bool small_path = true;
+};
+
+namespace {
+
+// ---- parameter transforms (gpccfixdelay_marginaliseb.jl:112-126; MiscUtil presumed) ---------------
+inline double softplus(double x) { return x > 0 ? x + std::log1p(std::exp(-x)) : std::log1p(std::exp(x)); }
+inline double logistic(double x) { return 0.5 * (1.0 + std::tanh(0.5 * x)); }
+
+void unpack_theta(const double* theta, int L, const gpcc_fit_options& o, double* alpha, double* rho, double* jac) {
+    for (int l = 0; l < L; ++l) {
+        alpha[l] = softplus(theta[l]) + o.alpha_floor;                       // makeα (:112)
+        if (jac) jac[l] = logistic(theta[l]);
+    }
+    const double s = logistic(theta[L]);
+    *rho = o.rhomin + (o.rhomax - o.rhomin) * s;                             // makeρ (:114)
+    if (jac) jac[L] = (o.rhomax - o.rhomin) * s * (1.0 - s);
+}
+
+int check_options(const gpcc_fit_options* o) {
+    if (!o) return fail(-1, "options pointer is NULL");
+    if (o->transform_id != GPCC_TRANSFORM_SOFTPLUS_LOGISTIC) return fail(-2, "unknown transform_id");
+    if (!(o->rhomin > 0) || !(o->rhomax > o->rhomin)) return fail(-3, "need 0 < rhomin < rhomax");
+    if (!(o->alpha_floor >= 0)) return fail(-4, "alpha_floor must be >= 0");
+    return 0;
+}
+
+// Evaluate `M` (delay, alpha, rho) triples that already sit in the pinned host mirrors of `s`.
+// Results land in s.ll.h / s.grad.h / s.info.h.
+int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv = nullptr,
+                       double* dump_a = nullptr) {
+    DeviceState& s = p->ctx->ds[di];
+    const int L = p->L;
+    CUDA_TRY(cudaSetDevice(s.dev));
+    CUDA_TRY(cudaMemcpyAsync(s.delays.d, s.delays.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.alpha.d, s.alpha.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.rho.d, s.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    EvalBatch b;
+    b.M = M; b.delays = s.delays.d; b.alpha = s.alpha.d; b.rho = s.rho.d; b.want_grad = want_grad;
+    b.ll = s.ll.d; b.grad = s.grad.d; b.info = s.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a;
+    const bool prof = p->ctx->profiling;
+    if (p->small_path) {
+        if (prof) CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
+        CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, s.stream));
+        if (prof) CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
+        s.launches += 1;
+    } else {
+        LargeTimings lt;
+        CUDA_TRY(large_eval(p->pd[di].dp, b, s.large, s.stream, prof, &lt));
+        s.launches += lt.launches;
+        s.ms_assembly += lt.ms_assembly; s.ms_factor += lt.ms_factor; s.ms_gradreduce += lt.ms_gradreduce;
+        s.ms_eval += lt.ms_assembly + lt.ms_factor + lt.ms_gradreduce;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s.ll.h, s.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    if (want_grad)
+        CUDA_TRY(cudaMemcpyAsync(s.grad.h, s.grad.d, (size_t)M * (L + 1) * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.info.h, s.info.d, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (prof && p->small_path) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        s.ms_eval += ms;
+    }
+    s.evals += M;
+    if (want_grad) s.evals_grad += M;
+    return 0;
+}
+
+int reserve_eval(gpcc_problem* p, int di, size_t M) {
+    DeviceState& s = p->ctx->ds[di];
+    const int L = p->L;
+    CUDA_TRY(cudaSetDevice(s.dev));
+    CUDA_TRY(s.delays.reserve(M * L));
+    CUDA_TRY(s.alpha.reserve(M * L));
+    CUDA_TRY(s.rho.reserve(M));
+    CUDA_TRY(s.ll.reserve(M));
+    CUDA_TRY(s.grad.reserve(M * (L + 1)));
+    CUDA_TRY(s.info.reserve(M));
+    return 0;
+}
+
+void reset_stats(gpcc_ctx* ctx) {
+    for (auto& s : ctx->ds) {
+        s.ms_eval = s.ms_assembly = s.ms_factor = s.ms_gradreduce = 0;
+        s.launches = s.evals = s.evals_grad = 0;
+    }
+}
+
+void collect_stats(gpcc_ctx* ctx, const gpcc_problem* p, double ms_total) {
+    gpcc_stats st{};
+    st.ms_total = ms_total;
+    for (auto& s : ctx->ds) {
+        st.ms_eval_kernels = std::max(st.ms_eval_kernels, s.ms_eval);   // devices run concurrently
+        st.ms_assembly = std::max(st.ms_assembly, s.ms_assembly);
+        st.ms_factor = std::max(st.ms_factor, s.ms_factor);
+        st.ms_gradreduce = std::max(st.ms_gradreduce, s.ms_gradreduce);
+        st.n_eval_launches += s.launches;
+        st.n_evals += s.evals;
+        st.n_evals_grad += s.evals_grad;
+    }
+    st.path = (p && !p->small_path) ? 1 : 0;
+    st.n_devices = (int)ctx->ds.size();
+    ctx->stats = st;
+}
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// ---- the fit of one device's shard ------------------------------------------------------------------
+struct FitOutputs {
+    double *ll, *theta, *alpha, *rho;
+    int *iters, *nfev, *info;
+};
+
+// Candidates idx[0..n) (global indices) are fitted on device `di`.
+int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double* delays, int P, const double* theta0,
+              const gpcc_fit_options& o, const FitOutputs& out) {
+    const int L = p->L, n = L + 1;
+    const int m = (int)idx.size();
+    if (m == 0) return 0;
+    DeviceState& s = p->ctx->ds[di];
+    LbfgsOptions lo;
+    lo.max_iter = o.max_iter; lo.gtol = o.gtol; lo.ftol = o.ftol; lo.history = o.history;
+
+    std::vector<LbfgsState> st(m);
+    // ---- stage 1: screening of the P start points (:207-209), batched over all candidates -----------
+    // chunked so that one batch never exceeds ~1M evaluations worth of staging
+    const size_t chunk_c = std::max<size_t>(1, std::min<size_t>(m, (size_t)(1 << 18) / std::max(1, P)));
+    int rc = reserve_eval(p, di, chunk_c * P);
+    if (rc) return rc;
+    std::vector<double> jac(n);
+    for (size_t c0 = 0; c0 < (size_t)m; c0 += chunk_c) {
+        const size_t c1 = std::min<size_t>(m, c0 + chunk_c);
+        for (size_t c = c0; c < c1; ++c) {
+            const int gi = idx[c];
+            for (int j = 0; j < P; ++j) {
+                const size_t e = (c - c0) * P + j;
+                const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + j) * n : theta0 + (size_t)j * n;
+                std::memcpy(s.delays.h + e * L, delays + (size_t)gi * L, L * sizeof(double));
+                unpack_theta(th, L, o, s.alpha.h + e * L, s.rho.h + e, nullptr);
+            }
+        }
+        rc = evaluate_on_device(p, di, (int)((c1 - c0) * P), 1);
+        if (rc) return rc;
+        for (size_t c = c0; c < c1; ++c) {
+            const int gi = idx[c];
+            int best = -1;
+            double bestf = std::numeric_limits<double>::infinity();
+            for (int j = 0; j < P; ++j) {          // argmin of -logL, first minimum wins (Julia argmin, :209)
+                const size_t e = (c - c0) * P + j;
+                const double f = -s.ll.h[e];
+                if (s.info.h[e] == 0 && std::isfinite(f) && f < bestf) { bestf = f; best = j; }
+            }
+            LbfgsState& S = st[c];
+            S.n = n;
+            S.nfev = P;
+            if (best < 0) { S.status = LbfgsState::NO_START; S.f = std::numeric_limits<double>::infinity(); continue; }
+            const size_t e = (c - c0) * P + best;
+            const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + best) * n : theta0 + (size_t)best * n;
+            double a_[LBFGS_MAXN], r_, g_[LBFGS_MAXN];
+            unpack_theta(th, L, o, a_, &r_, jac.data());
+            for (int k = 0; k < n; ++k) g_[k] = -s.grad.h[e * n + k] * jac[k];
+            S.start(n, th, bestf, g_, lo);
+        }
+    }
+    // ---- stage 2: batched L-BFGS ----------------------------------------------------------------------
+    std::vector<int> active;
+    active.reserve(m);
+    for (int c = 0; c < m; ++c) if (st[c].status == LbfgsState::RUNNING) active.push_back(c);
+    rc = reserve_eval(p, di, active.size());
+    if (rc) return rc;
+    while (!active.empty()) {
+        const int na = (int)active.size();
+        for (int a = 0; a < na; ++a) {
+            const int c = active[a];
+            std::memcpy(s.delays.h + (size_t)a * L, delays + (size_t)idx[c] * L, L * sizeof(double));
+            unpack_theta(st[c].xt, L, o, s.alpha.h + (size_t)a * L, s.rho.h + a, nullptr);
+        }
+        rc = evaluate_on_device(p, di, na, 1);
+        if (rc) return rc;
+        size_t w = 0;
+        for (int a = 0; a < na; ++a) {
+            const int c = active[a];
+            LbfgsState& S = st[c];
+            double a_[LBFGS_MAXN], r_, g_[LBFGS_MAXN];
+            unpack_theta(S.xt, L, o, a_, &r_, jac.data());
+            const bool ok = s.info.h[a] == 0 && std::isfinite(s.ll.h[a]);
+            for (int k = 0; k < n; ++k) g_[k] = ok ? -s.grad.h[(size_t)a * n + k] * jac[k] : 0.0;
+            S.feed(ok, -s.ll.h[a], g_, lo);
+            if (S.status == LbfgsState::RUNNING) active[w++] = c;
+        }
+        active.resize(w);
+    }
+    // ---- outputs ------------------------------------------------------------------------------------------
+    for (int c = 0; c < m; ++c) {
+        const int gi = idx[c];
+        const LbfgsState& S = st[c];
+        if (out.ll) out.ll[gi] = -S.f;                                         // -result.minimum (:351)
+        if (out.iters) out.iters[gi] = S.iters;
+        if (out.nfev) out.nfev[gi] = S.nfev;
+        if (out.info) out.info[gi] = S.status;
+        double a_[LBFGS_MAXN], r_ = std::numeric_limits<double>::quiet_NaN();
+        if (S.status == LbfgsState::NO_START) {
+            for (int k = 0; k < L; ++k) a_[k] = std::numeric_limits<double>::quiet_NaN();
+            if (out.theta) for (int k = 0; k < n; ++k) out.theta[(size_t)gi * n + k] = std::numeric_limits<double>::quiet_NaN();
+        } else {
+            unpack_theta(S.x, L, o, a_, &r_, nullptr);                          // unpack(paramopt) (:235)
+            if (out.theta) std::memcpy(out.theta + (size_t)gi * n, S.x, n * sizeof(double));
+        }
+        if (out.alpha) std::memcpy(out.alpha + (size_t)gi * L, a_, L * sizeof(double));
+        if (out.rho) out.rho[gi] = r_;
+    }
+    return 0;
+}
+
+// Run fn(di) on every device of the context concurrently (one host thread per device).
+template <class F>
+int for_each_device(gpcc_ctx* ctx, F fn) {
+    const int nd = (int)ctx->ds.size();
+    if (nd == 1) return fn(0);
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (int di = 0; di < nd; ++di)
+        th.emplace_back([&, di]() { rcs[di] = fn(di); errs[di] = g_last_error; });
+    for (auto& t : th) t.join();
+    for (int di = 0; di < nd; ++di)
+        if (rcs[di]) return fail(rcs[di], "device " + std::to_string(ctx->ds[di].dev) + ": " + errs[di]);
+    return 0;
+}
+
+int fit_all(gpcc_problem* p, int M, const double* delays, int P, const double* theta0, const gpcc_fit_options& o,
+            const FitOutputs& out) {
+    gpcc_ctx* ctx = p->ctx;
+    const int nd = (int)ctx->ds.size();
+    std::vector<std::vector<int>> shard(nd);
+    for (int m = 0; m < M; ++m) shard[m % nd].push_back(m);     // candidate m -> device m mod ndev
+    return for_each_device(ctx, [&](int di) { return fit_shard(p, di, shard[di], delays, P, theta0, o, out); });
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int gpcc_version(void) { return 100; }
+const char* gpcc_last_error(void) { return g_last_error.c_str(); }
+
+int gpcc_fit_options_default(gpcc_fit_options* o) {
+    if (!o) return fail(-1, "options pointer is NULL");
+    o->max_iter = 1000;
+    o->rhomin = 0.1;
+    o->rhomax = 20.0;
+    o->alpha_floor = 1e-8;
+    o->gtol = 1e-7;
+    o->ftol = 1e-13;
+    o->history = 8;
+    o->transform_id = GPCC_TRANSFORM_SOFTPLUS_LOGISTIC;
+    o->theta0_per_candidate = 0;
+    return 0;
+}
+
+int gpcc_ctx_create(int ndev, const int* dev_ids, gpcc_ctx** out) {
+    if (!out) return fail(-1, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(1000 + (int)e, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                       cudaGetErrorString(e));
+    }
+    if (ndev <= 0) ndev = 1;
+    if (ndev > count) return fail(-2, "ndev exceeds the number of visible CUDA devices");
+    gpcc_ctx* ctx = new gpcc_ctx();
+    ctx->ds.resize(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        DeviceState& s = ctx->ds[i];
+        s.dev = dev_ids ? dev_ids[i] : i;
+        if (s.dev < 0 || s.dev >= count) { delete ctx; return fail(-3, "invalid device id"); }
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, s.dev));
+        if (prop.major < 10) { delete ctx; return fail(-4, "libgpcc_b200 is built for sm_100a (Blackwell B200) only"); }
+        CUDA_TRY(cudaSetDevice(s.dev));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&s.ev0));
+        CUDA_TRY(cudaEventCreate(&s.ev1));
+    }
+    *out = ctx;
+    return 0;
+}
+
+int gpcc_ctx_destroy(gpcc_ctx* ctx) {
+    if (!ctx) return 0;
+    if (ctx->nccl) nccl_bridge_destroy(ctx->nccl);
+    for (auto& s : ctx->ds) {
+        cudaSetDevice(s.dev);
+        s.delays.release(); s.alpha.release(); s.rho.release(); s.ll.release(); s.grad.release(); s.info.release();
+        large_workspace_release(s.large);
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete ctx;
+    return 0;
+}
+
+int gpcc_ctx_set_profiling(gpcc_ctx* ctx, int enabled) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    ctx->profiling = enabled != 0;
+    return 0;
+}
+int gpcc_ctx_get_stats(const gpcc_ctx* ctx, gpcc_stats* out) {
+    if (!ctx || !out) return fail(-1, "NULL argument");
+    *out = ctx->stats;
+    return 0;
+}
+int gpcc_ctx_device_count(const gpcc_ctx* ctx) { return ctx ? (int)ctx->ds.size() : 0; }
+
+int gpcc_problem_create(gpcc_ctx* ctx, int L, const int* n_per_band, const double* t, const double* y,
+                        const double* sigma, int kernel_id, const double* mub, const double* Sigmab,
+                        gpcc_problem** out) {
+    if (!ctx || !out || !n_per_band || !t || !y || !sigma) return fail(-1, "NULL argument");
+    *out = nullptr;
+    if (L < 1 || L > GPCC_MAX_BANDS) return fail(-2, "L must be in 1..GPCC_MAX_BANDS");
+    if (kernel_id < 0 || kernel_id > 3)
+        return fail(-3, "unknown kernel (expected GPCC.OU, GPCC.rbf, GPCC.matern32 or GPCC.matern52)");
+    gpcc_problem* p = new gpcc_problem();
+    p->ctx = ctx; p->L = L; p->kernel_id = kernel_id;
+    p->n_per_band.assign(n_per_band, n_per_band + L);
+    p->band_start.assign(L + 1, 0);
+    for (int l = 0; l < L; ++l) {
+        if (n_per_band[l] < 1) { delete p; return fail(-4, "every band needs at least one observation"); }
+        p->band_start[l + 1] = p->band_start[l] + n_per_band[l];
+    }
+    const int N = p->N = p->band_start[L];
+    p->t.assign(t, t + N); p->y.assign(y, y + N); p->sigma.assign(sigma, sigma + N);
+    p->mub.resize(L); p->Sigmab.resize(L);
+    for (int l = 0; l < L; ++l) {
+        const int a = p->band_start[l], b = p->band_start[l + 1], n = b - a;
+        if (mub) p->mub[l] = mub[l];
+        else {                                           // mean(y_l)   (gpccfixdelay_marginaliseb.jl:92)
+            double s = 0; for (int i = a; i < b; ++i) s += y[i];
+            p->mub[l] = s / n;
+        }
+        if (Sigmab) p->Sigmab[l] = Sigmab[l];
+        else {                                           // 100*var(y_l), unbiased (:94)
+            double s = 0; for (int i = a; i < b; ++i) s += y[i];
+            const double mean = s / n;
+            double v = 0; for (int i = a; i < b; ++i) v += (y[i] - mean) * (y[i] - mean);
+            p->Sigmab[l] = n > 1 ? 100.0 * v / (n - 1) : std::numeric_limits<double>::quiet_NaN();
+        }
+        if (!(p->Sigmab[l] > 0) || !std::isfinite(p->mub[l])) {
+            delete p;
+            return fail(-5, "prior of the shift b is degenerate (band with <2 points or zero variance)");
+        }
+    }
+    p->band.resize(N); p->resid.resize(N); p->s2.resize(N); p->sigb.resize(N);
+    for (int l = 0; l < L; ++l)
+        for (int i = p->band_start[l]; i < p->band_start[l + 1]; ++i) {
+            p->band[i] = l;
+            p->resid[i] = y[i] - p->mub[l];              // Y - Q*mu_b (:98, :139)
+            p->s2[i] = sigma[i] * sigma[i];              // Sobs (:89)
+            p->sigb[i] = p->Sigmab[l];                   // B = Q Sigma_b Q' (:96)
+            if (!std::isfinite(t[i]) || !std::isfinite(y[i]) || !std::isfinite(sigma[i])) {
+                delete p;
+                return fail(-6, "non-finite input data");
+            }
+        }
+    p->small_path = small_path_supports(N);
+    p->pd.resize(ctx->ds.size());
+    for (size_t di = 0; di < ctx->ds.size(); ++di) {
+        auto& d = p->pd[di];
+        CUDA_TRY(cudaSetDevice(ctx->ds[di].dev));
+        CUDA_TRY(cudaMalloc(&d.t, N * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.resid, N * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.s2, N * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.sigb, N * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.band, N * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(d.t, p->t.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.resid, p->resid.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.s2, p->s2.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.sigb, p->sigb.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.band, p->band.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+        d.dp.N = N; d.dp.L = L; d.dp.kernel_id = kernel_id;
+        d.dp.t = d.t; d.dp.resid = d.resid; d.dp.s2 = d.s2; d.dp.sigb = d.sigb; d.dp.band = d.band;
+        for (int l = 0; l <= L; ++l) d.dp.band_start[l] = p->band_start[l];
+    }
+    *out = p;
+    return 0;
+}
+
+int gpcc_problem_destroy(gpcc_problem* p) {
+    if (!p) return 0;
+    for (size_t di = 0; di < p->pd.size(); ++di) {
+        cudaSetDevice(p->ctx->ds[di].dev);
+        auto& d = p->pd[di];
+        cudaFree(d.t); cudaFree(d.resid); cudaFree(d.s2); cudaFree(d.sigb); cudaFree(d.band);
+    }
+    delete p;
+    return 0;
+}
+
+int gpcc_problem_get_prior(const gpcc_problem* p, double* mub, double* Sigmab) {
+    if (!p) return fail(-1, "problem is NULL");
+    if (mub) std::memcpy(mub, p->mub.data(), p->L * sizeof(double));
+    if (Sigmab) std::memcpy(Sigmab, p->Sigmab.data(), p->L * sizeof(double));
+    return 0;
+}
+
+static int loglik_batch_impl(gpcc_problem* p, int M, const double* delays, const double* alpha, const double* rho,
+                             const double* theta, const gpcc_fit_options* o, int want_grad, double* out_ll,
+                             double* out_grad, int* out_info) {
+    if (!p || !delays || !out_ll) return fail(-1, "NULL argument");
+    if (M < 0) return fail(-2, "M < 0");
+    if (want_grad && !out_grad) return fail(-3, "want_grad set but out_grad is NULL");
+    if (M == 0) return 0;
+    const int L = p->L, n = L + 1;
+    if (!theta) {
+        // delayedCovariance.jl:3-7: scale > 0 is asserted and rho <= 0 is an error.  The reference wraps the
+        // objective in `safewrapper` (:153), i.e. the optimiser sees a penalty instead of the exception; here
+        // such rows get info = -1 and loglik = -Inf and are not sent to the device.
+    }
+    gpcc_ctx* ctx = p->ctx;
+    Timer tm;
+    reset_stats(ctx);
+    const int nd = (int)ctx->ds.size();
+    const size_t chunk = 1 << 18;
+    int rc = for_each_device(ctx, [&](int di) -> int {
+        DeviceState& s = ctx->ds[di];
+        std::vector<int> mine;
+        for (int m = di; m < M; m += nd) mine.push_back(m);
+        std::vector<double> jac(n);
+        for (size_t c0 = 0; c0 < mine.size(); c0 += chunk) {
+            const size_t c1 = std::min(mine.size(), c0 + chunk);
+            int r = reserve_eval(p, di, c1 - c0);
+            if (r) return r;
+            std::vector<int> sent;
+            sent.reserve(c1 - c0);
+            for (size_t c = c0; c < c1; ++c) {
+                const int m = mine[c];
+                const size_t e = sent.size();
+                bool valid = true;
+                if (theta) {
+                    unpack_theta(theta + (size_t)m * n, L, *o, s.alpha.h + e * L, s.rho.h + e, nullptr);
+                } else {
+                    std::memcpy(s.alpha.h + e * L, alpha + (size_t)m * L, L * sizeof(double));
+                    s.rho.h[e] = rho[m];
+                }
+                for (int l = 0; l < L; ++l) valid = valid && (s.alpha.h[e * L + l] > 0) && std::isfinite(s.alpha.h[e * L + l]);
+                valid = valid && (s.rho.h[e] > 0) && std::isfinite(s.rho.h[e]);
+                for (int l = 0; l < L; ++l) valid = valid && std::isfinite(delays[(size_t)m * L + l]);
+                if (!valid) {
+                    out_ll[m] = -std::numeric_limits<double>::infinity();
+                    if (out_info) out_info[m] = -1;
+                    if (want_grad) for (int k = 0; k < n; ++k) out_grad[(size_t)m * n + k] = 0.0;
+                    continue;
+                }
+                std::memcpy(s.delays.h + e * L, delays + (size_t)m * L, L * sizeof(double));
+                sent.push_back(m);
+            }
+            if (sent.empty()) continue;
+            r = evaluate_on_device(p, di, (int)sent.size(), want_grad);
+            if (r) return r;
+            for (size_t e = 0; e < sent.size(); ++e) {
+                const int m = sent[e];
+                out_ll[m] = s.ll.h[e];
+                if (out_info) out_info[m] = s.info.h[e];
+                if (want_grad) {
+                    if (theta) {
+                        double a_[LBFGS_MAXN], r_;
+                        unpack_theta(theta + (size_t)m * n, L, *o, a_, &r_, jac.data());
+                        for (int k = 0; k < n; ++k) out_grad[(size_t)m * n + k] = s.grad.h[e * n + k] * jac[k];
+                    } else {
+                        std::memcpy(out_grad + (size_t)m * n, s.grad.h + e * n, n * sizeof(double));
+                    }
+                }
+            }
+        }
+        return 0;
+    });
+    collect_stats(ctx, p, tm.ms());
+    return rc;
+}
+
+int gpcc_loglik_batch(gpcc_problem* p, int M, const double* delays, const double* alpha, const double* rho,
+                      int want_grad, double* out_ll, double* out_grad, int* out_info) {
+    if (!alpha || !rho) return fail(-1, "NULL argument");
+    return loglik_batch_impl(p, M, delays, alpha, rho, nullptr, nullptr, want_grad, out_ll, out_grad, out_info);
+}
+
+int gpcc_loglik_theta_batch(gpcc_problem* p, int M, const double* delays, const double* theta,
+                            const gpcc_fit_options* opt, int want_grad, double* out_ll, double* out_grad,
+                            int* out_info) {
+    if (!theta) return fail(-1, "NULL argument");
+    int rc = check_options(opt);
+    if (rc) return rc;
+    return loglik_batch_impl(p, M, delays, nullptr, nullptr, theta, opt, want_grad, out_ll, out_grad, out_info);
+}
+
+int gpcc_fit_batch(gpcc_problem* p, int M, const double* delays, int P, const double* theta0,
+                   const gpcc_fit_options* opt, double* out_ll, double* out_theta, double* out_alpha,
+                   double* out_rho, int* out_iters, int* out_nfev, int* out_info) {
+    if (!p || !delays || !theta0) return fail(-1, "NULL argument");
+    int rc = check_options(opt);
+    if (rc) return rc;
+    if (M < 0 || P < 1) return fail(-2, "need M >= 0 and P >= 1");
+    if (M == 0) return 0;
+    for (size_t i = 0; i < (size_t)M * p->L; ++i)
+        if (!std::isfinite(delays[i])) return fail(-3, "non-finite delay");
+    Timer tm;
+    reset_stats(p->ctx);
+    FitOutputs out{out_ll, out_theta, out_alpha, out_rho, out_iters, out_nfev, out_info};
+    rc = fit_all(p, M, delays, P, theta0, *opt, out);
+    collect_stats(p->ctx, p, tm.ms());
+    return rc;
+}
+
+int gpcc_grid_posterior(gpcc_problem* p, int M, const double* delays, const double* logprior, int P,
+                        const double* theta0, const gpcc_fit_options* opt, double* out_ll, double* out_post,
+                        double* out_theta, double* out_alpha, double* out_rho, int* out_nfev, int* out_info) {
+    if (!p || !delays || !theta0 || !out_post) return fail(-1, "NULL argument");
+    int rc = check_options(opt);
+    if (rc) return rc;
+    if (M < 1 || P < 1) return fail(-2, "need M >= 1 and P >= 1");
+    Timer tm;
+    reset_stats(p->ctx);
+    std::vector<double> ll_local;
+    double* ll = out_ll;
+    if (!ll) { ll_local.resize(M); ll = ll_local.data(); }
+    FitOutputs out{ll, out_theta, out_alpha, out_rho, nullptr, out_nfev, out_info};
+    rc = fit_all(p, M, delays, P, theta0, *opt, out);
+    if (rc) return rc;
+    // allgather of the per-device slices (NCCL when the context spans several devices) + log-sum-exp on device
+    rc = posterior_on_devices(p->ctx, M, ll, logprior, out_post);
+    collect_stats(p->ctx, p, tm.ms());
+    return rc;
+}
+
+int gpcc_getprobabilities(gpcc_ctx* ctx, int M, const double* loglik, const double* logprior, double* out_post) {
+    if (!ctx || !loglik || !out_post) return fail(-1, "NULL argument");
+    if (M < 1) return fail(-2, "M < 1");
+    DeviceState& s = ctx->ds[0];
+    CUDA_TRY(cudaSetDevice(s.dev));
+    double *d_ll = nullptr, *d_pr = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ll, M * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_out, M * sizeof(double)));
+    if (logprior) CUDA_TRY(cudaMalloc(&d_pr, M * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(d_ll, loglik, M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    if (logprior) CUDA_TRY(cudaMemcpyAsync(d_pr, logprior, M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(posterior_launch(M, d_ll, d_pr, d_out, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(out_post, d_out, M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    cudaFree(d_ll); cudaFree(d_out); if (d_pr) cudaFree(d_pr);
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- posterior over the grid: allgather + log-sum-exp ---------------------------------------------------
+namespace gpcc {
+
+int posterior_on_devices(gpcc_ctx* ctx, int M, const double* ll, const double* logprior, double* out_post) {
+    const int nd = (int)ctx->ds.size();
+    if (nd == 1) return gpcc_getprobabilities(ctx, M, ll, logprior, out_post);
+    // Each device owns the strided slice m = di, di+nd, ... ; pad to a common length, allgather over NVLink,
+    // then device 0 normalises (src/getprobabilities.jl:14-16).
+    const int per = (M + nd - 1) / nd;
+    if (!ctx->nccl) {
+        std::vector<int> devs;
+        for (auto& s : ctx->ds) devs.push_back(s.dev);
+        std::string err;
+        ctx->nccl = nccl_bridge_create(devs, err);
+        if (!ctx->nccl) return fail(2000, "NCCL unavailable for the multi-device allgather: " + err);
+    }
+    std::vector<double*> d_send(nd, nullptr), d_recv(nd, nullptr);
+    std::vector<cudaStream_t> streams(nd);
+    const double ninf = -std::numeric_limits<double>::infinity();
+    for (int di = 0; di < nd; ++di) {
+        DeviceState& s = ctx->ds[di];
+        CUDA_TRY(cudaSetDevice(s.dev));
+        CUDA_TRY(cudaMalloc(&d_send[di], per * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d_recv[di], (size_t)per * nd * sizeof(double)));
+        std::vector<double> slice(per, ninf);
+        for (int k = 0; k < per; ++k) {
+            const int m = di + k * nd;
+            if (m < M) slice[k] = ll[m] + (logprior ? logprior[m] : 1.0);      // joint (getprobabilities.jl:3,14)
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_send[di], slice.data(), per * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        streams[di] = s.stream;
+    }
+    std::string err;
+    if (nccl_bridge_allgather(ctx->nccl, d_send, d_recv, per, streams, err)) return fail(2001, "ncclAllGather: " + err);
+    // gathered layout: [rank][k] -> candidate m = rank + k*nd
+    DeviceState& s0 = ctx->ds[0];
+    CUDA_TRY(cudaSetDevice(s0.dev));
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)per * nd * sizeof(double)));
+    CUDA_TRY(posterior_launch(per * nd, d_recv[0], nullptr, d_out, s0.stream, /*joint_already=*/true));
+    std::vector<double> tmp((size_t)per * nd);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+    CUDA_TRY(cudaStreamSynchronize(s0.stream));
+    for (int di = 0; di < nd; ++di)
+        for (int k = 0; k < per; ++k) {
+            const int m = di + k * nd;
+            if (m < M) out_post[m] = tmp[(size_t)di * per + k];
+        }
+    cudaFree(d_out);
+    for (int di = 0; di < nd; ++di) {
+        cudaSetDevice(ctx->ds[di].dev);
+        cudaFree(d_send[di]); cudaFree(d_recv[di]);
+    }
+    return 0;
+}
+
+}  // namespace gpcc

@@ -1,0 +1,164 @@
+// Host-driven batched L-BFGS: one small state machine per delay candidate; every round the driver
+// gathers the trial points of all active candidates into ONE batched device evaluation
+// (likelihood + analytic gradient) and feeds the results back.  Replaces the per-candidate
+// optimize(..., NelderMead(), ...) of /root/reference/src/gpccfixdelay_marginaliseb.jl:205-211
+// as north_star specifies.  Minimises f = -logL over the unconstrained theta in R^(L+1).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace gpcc {
+
+constexpr int LBFGS_MAXN = 9;    // L+1 <= GPCC_MAX_BANDS+1
+constexpr int LBFGS_MAXM = 16;
+
+struct LbfgsOptions {
+    int max_iter = 1000;
+    double gtol = 1e-7;
+    double ftol = 1e-13;
+    int history = 8;
+    int max_ls = 30;
+};
+
+struct LbfgsState {
+    enum Status { RUNNING = -100, CONVERGED = 0, ITER_CAP = 1, LS_STALL = 2, NO_START = -1 };
+    int n = 0;
+    int status = RUNNING;
+    int iters = 0, nfev = 0;
+    double x[LBFGS_MAXN], g[LBFGS_MAXN], f = 0.0;
+    double d[LBFGS_MAXN], xt[LBFGS_MAXN];
+    double t = 1.0, tlo = 0.0, thi = 0.0, gd0 = 0.0;
+    int ls_trials = 0;
+    bool have_fb = false;              // best Armijo point seen in this line search (fallback)
+    double fb_x[LBFGS_MAXN], fb_g[LBFGS_MAXN], fb_f = 0.0;
+    double S[LBFGS_MAXM][LBFGS_MAXN], Y[LBFGS_MAXM][LBFGS_MAXN], R[LBFGS_MAXM];
+    int hcount = 0, hhead = 0;         // ring buffer
+    int small_df = 0;
+
+    static double dot(const double* a, const double* b, int n) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += a[i] * b[i];
+        return s;
+    }
+
+    void start(int n_, const double* x0, double f0, const double* g0, const LbfgsOptions& o) {
+        n = n_;
+        std::memcpy(x, x0, n * sizeof(double));
+        std::memcpy(g, g0, n * sizeof(double));
+        f = f0;
+        status = RUNNING;
+        iters = 0;
+        hcount = hhead = 0;
+        small_df = 0;
+        double gmax = 0.0;
+        for (int i = 0; i < n; ++i) gmax = std::fmax(gmax, std::fabs(g[i]));
+        if (!(gmax > o.gtol)) { status = CONVERGED; return; }
+        if (o.max_iter <= 0) { status = ITER_CAP; return; }
+        new_direction(true);
+    }
+
+    void new_direction(bool first) {
+        // two-loop recursion
+        double qv[LBFGS_MAXN], a[LBFGS_MAXM];
+        for (int i = 0; i < n; ++i) qv[i] = g[i];
+        for (int k = 0; k < hcount; ++k) {
+            const int idx = (hhead - 1 - k + 2 * LBFGS_MAXM) % LBFGS_MAXM;
+            a[k] = R[idx] * dot(S[idx], qv, n);
+            for (int i = 0; i < n; ++i) qv[i] -= a[k] * Y[idx][i];
+        }
+        if (hcount > 0) {
+            const int idx = (hhead - 1 + LBFGS_MAXM) % LBFGS_MAXM;
+            const double gamma = 1.0 / (R[idx] * dot(Y[idx], Y[idx], n));
+            for (int i = 0; i < n; ++i) qv[i] *= gamma;
+        }
+        for (int k = hcount - 1; k >= 0; --k) {
+            const int idx = (hhead - 1 - k + 2 * LBFGS_MAXM) % LBFGS_MAXM;
+            const double bb = R[idx] * dot(Y[idx], qv, n);
+            for (int i = 0; i < n; ++i) qv[i] += (a[k] - bb) * S[idx][i];
+        }
+        for (int i = 0; i < n; ++i) d[i] = -qv[i];
+        gd0 = dot(g, d, n);
+        if (!(gd0 < 0.0) || !std::isfinite(gd0)) {     // not a descent direction: restart from steepest descent
+            hcount = 0;
+            for (int i = 0; i < n; ++i) d[i] = -g[i];
+            gd0 = dot(g, d, n);
+            first = true;
+        }
+        t = 1.0;
+        if (first || hcount == 0) {
+            const double gn = std::sqrt(dot(g, g, n));
+            t = std::fmin(1.0, 1.0 / gn);
+        }
+        tlo = 0.0;
+        thi = std::numeric_limits<double>::infinity();
+        ls_trials = 0;
+        have_fb = false;
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + t * d[i];
+    }
+
+    void accept(const double* xn, double fn, const double* gn, const LbfgsOptions& o, int hist) {
+        double s[LBFGS_MAXN], y[LBFGS_MAXN];
+        for (int i = 0; i < n; ++i) { s[i] = xn[i] - x[i]; y[i] = gn[i] - g[i]; }
+        const double sy = dot(s, y, n);
+        if (sy > 1e-10 * std::sqrt(dot(s, s, n) * dot(y, y, n)) && sy > 0.0) {
+            std::memcpy(S[hhead], s, n * sizeof(double));
+            std::memcpy(Y[hhead], y, n * sizeof(double));
+            R[hhead] = 1.0 / sy;
+            hhead = (hhead + 1) % LBFGS_MAXM;
+            if (hcount < hist) ++hcount;
+        }
+        const double df = f - fn;
+        std::memcpy(x, xn, n * sizeof(double));
+        std::memcpy(g, gn, n * sizeof(double));
+        f = fn;
+        ++iters;
+        double gmax = 0.0;
+        for (int i = 0; i < n; ++i) gmax = std::fmax(gmax, std::fabs(g[i]));
+        if (gmax <= o.gtol) { status = CONVERGED; return; }
+        if (df <= o.ftol * std::fmax(1.0, std::fabs(f))) { if (++small_df >= 2) { status = CONVERGED; return; } }
+        else small_df = 0;
+        if (iters >= o.max_iter) { status = ITER_CAP; return; }
+        new_direction(false);
+    }
+
+    // Feed the evaluation at xt (ok=false: matrix not PD / non-finite).  Afterwards either status != RUNNING
+    // or xt holds the next trial point.
+    void feed(bool ok, double ft, const double* gt, const LbfgsOptions& o) {
+        ++nfev;
+        ++ls_trials;
+        const int hist = o.history < 1 ? 1 : (o.history > LBFGS_MAXM ? LBFGS_MAXM : o.history);
+        const double c1 = 1e-4, c2 = 0.9;
+        bool armijo = ok && std::isfinite(ft) && ft <= f + c1 * t * gd0;
+        if (armijo) {
+            const double gtd = dot(gt, d, n);
+            if (gtd >= c2 * gd0) { accept(xt, ft, gt, o, hist); return; }   // weak Wolfe holds
+            if (!have_fb || ft < fb_f) {
+                have_fb = true; fb_f = ft;
+                std::memcpy(fb_x, xt, n * sizeof(double));
+                std::memcpy(fb_g, gt, n * sizeof(double));
+            }
+            tlo = t;
+            t = std::isinf(thi) ? 2.0 * t : 0.5 * (tlo + thi);
+        } else {
+            thi = t;
+            double tn = 0.5 * (tlo + thi);
+            if (tlo == 0.0 && ok && std::isfinite(ft)) {     // quadratic interpolation through f(0), f'(0), f(t)
+                const double den = 2.0 * (ft - f - gd0 * t);
+                if (den > 0.0) {
+                    const double tq = -gd0 * t * t / den;
+                    tn = std::fmin(std::fmax(tq, 0.1 * t), 0.5 * t);
+                }
+            }
+            t = tn;
+        }
+        if (ls_trials >= o.max_ls || !(thi - tlo > 1e-16 * std::fmax(1.0, thi))) {
+            if (have_fb && fb_f < f) { accept(fb_x, fb_f, fb_g, o, hist); return; }
+            status = LS_STALL;
+            return;
+        }
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + t * d[i];
+    }
+};
+
+}  // namespace gpcc

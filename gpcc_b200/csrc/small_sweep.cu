@@ -1,0 +1,399 @@
+// Fused small-N evaluator: one CTA per (delay candidate, hyper-parameter) pair.
+//
+// Replaces, for N+1 <= 8*SMALL_MAX_T, the reference's objective
+//   K = delayedCovariance(kernel, alpha, tau, rho, tarray) + Sobs + B ; logpdf(MvNormal(bbar, K), Y)
+// (/root/reference/src/gpccfixdelay_marginaliseb.jl:133-141, src/delayedCovariance.jl:1-38) and adds
+// the analytic gradient 0.5 tr((a a' - K^-1) dK/dtheta) that north_star asks for.
+//
+// Design (B200: 64 FP64 FMA/clk/SM, 64K registers/SM, smem 128 B/clk):
+//   * the lower triangle of the (N+1)x(N+1) bordered matrix [K~ r; r' 0] lives ENTIRELY IN REGISTERS,
+//     one 8x8 tile per thread (N=150 -> 190 threads x 64 doubles); nothing N^2-sized touches smem/HBM;
+//   * assembly is fused: every thread evaluates its 64 kernel entries from the shifted times in smem;
+//   * one symmetric Gauss-Jordan "sweep" per index k (k = 0..N-1): A_ij -= A_ik A_kj / A_kk for
+//     i,j != k, A_ik <- A_ik/A_kk, A_kk <- -1/A_kk.  Per step a thread does 64 independent DFMAs on its
+//     tile from 16 values broadcast through shared memory (8 LDS.128) and ONE __syncthreads: the
+//     owners publish column k+1 (double buffered) as soon as their slice of it is updated.
+//     The pivots are exactly the Cholesky pivots L_kk^2, so logdet = sum log(pivot) and the
+//     leading-minor `info` follow LAPACK dpotrf; the border row gives a = K~^-1 r and the corner
+//     -r'K~^-1 r by forward elimination; after N steps the tile registers hold -K~^-1.
+//     Work: N^3/2 DFMA = N^3 flop, the same as potrf + potri, but perfectly balanced, with no
+//     triangular solves and no second pass;
+//   * the gradient contracts W = a a' - K~^-1 against K and dK/drho recomputed on the fly (never
+//     stored), reduced deterministically (no atomics).
+#include "gpcc_internal.h"
+#include "kernfun.cuh"
+#include <climits>
+#include <cmath>
+
+namespace gpcc {
+
+namespace {
+
+constexpr int TS = SMALL_TILE;  // 8
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+
+__device__ __forceinline__ int cidx(int i, int T) {  // chunked layout: [pair-of-rows part][tile][2]
+    return ((i & 7) >> 1) * (2 * T) + ((i >> 3) << 1) + (i & 1);
+}
+__device__ __forceinline__ void load8(const double* buf, int tile, int T, double (&out)[8]) {
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+        const double2 v = *reinterpret_cast<const double2*>(buf + part * 2 * T + 2 * tile);
+        out[2 * part] = v.x;
+        out[2 * part + 1] = v.y;
+    }
+}
+__device__ __forceinline__ void store8(double* buf, int tile, int T, const double (&in)[8]) {
+#pragma unroll
+    for (int part = 0; part < 4; ++part)
+        *reinterpret_cast<double2*>(buf + part * 2 * T + 2 * tile) = make_double2(in[2 * part], in[2 * part + 1]);
+}
+
+// Publish column `kn` (tile tkn, in-tile index KKN) of the symmetric matrix for the next sweep step.
+template <int KKN>
+__device__ __forceinline__ void publish(const double (&A)[8][8], int ti, int tj, int tkn, int kn, int T,
+                                        double* nb, double* pslot, double* piv) {
+    if (tj == tkn) {
+        double vals[8];
+        if (ti == tkn) {  // diagonal tile: below the diagonal from the column, above it from the row
+#pragma unroll
+            for (int r = 0; r < 8; ++r) vals[r] = (r >= KKN) ? A[r][KKN] : A[KKN][r];
+            const double d = A[KKN][KKN];
+            piv[kn] = d;
+            *pslot = 1.0 / d;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) vals[r] = A[r][KKN];
+        }
+        store8(nb, ti, T, vals);
+    } else if (ti == tkn) {
+        double vals[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vals[c] = A[KKN][c];
+        store8(nb, tj, T, vals);
+    }
+}
+
+template <int KK>
+__device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, int tk, int k, int N, int T, int Np,
+                                           double* cbuf, double* pbuf, double* piv, bool active) {
+    const double* cb = cbuf + (k & 1) * Np;
+    double cr[8], v[8];
+    load8(cb, ti, T, cr);
+    load8(cb, tj, T, v);
+    const double pr = pbuf[k & 1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] *= pr;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) A[r][c] = fma(-cr[r], v[c], A[r][c]);
+    if (tj == tk) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) A[r][KK] = cr[r] * pr;
+    }
+    if (ti == tk) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) A[KK][c] = v[c];
+        if (tj == tk) A[KK][KK] = -pr;
+    }
+    const int kn = k + 1;
+    if (kn < N && active) {
+        double* nb = cbuf + (kn & 1) * Np;
+        if (KK < 7) publish<(KK + 1) & 7>(A, ti, tj, tk, kn, T, nb, pbuf + (kn & 1), piv);
+        else        publish<0>(A, ti, tj, tk + 1, kn, T, nb, pbuf + (kn & 1), piv);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum: xor-tree inside each warp, then thread 0 adds the warp totals in order.
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nthreads) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    const int nw = (nthreads + 31) >> 5;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    return s;
+}
+
+template <int KID, int MAXTHREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
+small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
+    extern __shared__ __align__(16) double smem[];
+    const int N = p.N, L = p.L;
+    const int Np = T * TS;
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int ntiles = T * (T + 1) / 2;
+    const bool active = tid < ntiles;
+    const int q = active ? tid : ntiles - 1;
+    int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > q) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+    const int tj = q - ti * (ti + 1) / 2;
+
+    double* tsh = smem;             // shifted times t_i - tau_band(i)         (chunk layout)
+    double* av = tsh + Np;          // alpha_band(i), 0 for padding            (chunk layout)
+    double* sbv = av + Np;          // Sigma_b[band(i)]                         (chunk layout)
+    double* dadd = sbv + Np;        // sigma_i^2                                (chunk layout)
+    double* cbuf = dadd + Np;       // 2 x broadcast column                     (chunk layout)
+    double* piv = cbuf + 2 * Np;    // pivots                                   (natural)
+    double* abuf = piv + Np;        // residual r, later a = K~^-1 r            (chunk layout)
+    double* pbuf = abuf + Np;       // 2 pivot reciprocals (+2 pad)
+    double* red = pbuf + 4;         // 64 reduction slots
+    double* part = red + 64;        // [T][T][8] gradient row-sum partials (gradient only)
+    int* bandv = reinterpret_cast<int*>(part + (b.want_grad ? T * T * 8 : 0));  // [Np] natural
+
+    const double rho = b.rho[e];
+    const KernParams kp = make_kern_params(KID, rho);
+
+    for (int i = tid; i < Np; i += nthreads) {
+        const int ci = cidx(i, T);
+        if (i < N) {
+            const int bi = p.band[i];
+            tsh[ci] = p.t[i] - b.delays[(size_t)e * L + bi];   // delayedCovariance.jl:27 (x - delays[l])
+            av[ci] = b.alpha[(size_t)e * L + bi];
+            sbv[ci] = p.sigb[i];
+            dadd[ci] = p.s2[i];
+            abuf[ci] = p.resid[i];
+            bandv[i] = bi;
+        } else {
+            tsh[ci] = 0.0; av[ci] = 0.0; sbv[ci] = 0.0; dadd[ci] = 0.0; abuf[ci] = 0.0;
+            bandv[i] = -1 - i;
+        }
+    }
+    __syncthreads();
+
+    // ---- assembly of the bordered matrix tile in registers --------------------------------------
+    double A[8][8];
+    {
+        double tc[8], ac[8], rc[8];
+        int bc[8];
+        load8(tsh, tj, T, tc);
+        load8(av, tj, T, ac);
+        load8(abuf, tj, T, rc);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bc[c] = bandv[tj * 8 + c];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = ti * 8 + r;
+            const int ci = cidx(i, T);
+            const double tr = tsh[ci], ar = av[ci], sbr = sbv[ci], dr = dadd[ci];
+            const int br = bandv[i];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = tj * 8 + c;
+                const double kv = kern_value<KID>(tr - tc[c], kp);
+                double val = (ar * ac[c]) * kv;          // scale[l]*scale[m]*kernel  (delayedCovariance.jl:27)
+                if (i == j) val += dr;                   // + Sobs                   (gpccfixdelay_marginaliseb.jl:135)
+                if (br == bc[c]) val += sbr;             // + B = Q Sigma_b Q'
+                if (i == N) val = rc[c];                 // border row: r = Y - bbar (corner = 0)
+                if (i > N && i == j) val = 1.0;          // padding
+                A[r][c] = val;
+            }
+        }
+    }
+    __syncthreads();   // everyone has read abuf/tsh before cbuf traffic starts (abuf is reused later)
+
+    // ---- publish column 0, then N sweep steps ----------------------------------------------------
+    if (active) publish<0>(A, ti, tj, 0, 0, T, cbuf, pbuf, piv);
+    __syncthreads();
+    for (int tk = 0; tk < T; ++tk) {
+        const int k0 = tk * 8;
+        if (k0 >= N) break;
+        sweep_step<0>(A, ti, tj, tk, k0 + 0, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 1 >= N) break;
+        sweep_step<1>(A, ti, tj, tk, k0 + 1, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 2 >= N) break;
+        sweep_step<2>(A, ti, tj, tk, k0 + 2, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 3 >= N) break;
+        sweep_step<3>(A, ti, tj, tk, k0 + 3, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 4 >= N) break;
+        sweep_step<4>(A, ti, tj, tk, k0 + 4, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 5 >= N) break;
+        sweep_step<5>(A, ti, tj, tk, k0 + 5, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 6 >= N) break;
+        sweep_step<6>(A, ti, tj, tk, k0 + 6, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 7 >= N) break;
+        sweep_step<7>(A, ti, tj, tk, k0 + 7, N, T, Np, cbuf, pbuf, piv, active);
+    }
+
+    // ---- log-determinant, info, quadratic form ---------------------------------------------------
+    const int tN = N >> 3, rN = N & 7;
+    double ld = 0.0;
+    int bad = INT_MAX;
+    for (int k = tid; k < N; k += nthreads) {
+        const double d = piv[k];
+        if (!(d > 0.0)) bad = min(bad, k + 1); else ld += log(d);
+    }
+    ld = block_sum(ld, red, tid, nthreads);
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = INT_MAX;
+    __syncthreads();
+    if (bad != INT_MAX) atomicMin(&s_bad, bad);   // min is order independent: deterministic
+    __syncthreads();
+    const int info = (s_bad == INT_MAX) ? 0 : s_bad;
+
+    if (active && ti == tN && tj == tN) {
+        double qv = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r == rN) qv = -A[r][r];
+        red[32] = qv;
+    }
+    __syncthreads();
+    const double quad = red[32];
+    const double ll = -0.5 * ((double)N * LOG2PI + ld + quad);   // logpdf(MvNormal(bbar,K), Y)  (:139)
+    if (tid == 0) {
+        b.ll[e] = info ? -INFINITY : ll;
+        if (b.info) b.info[e] = info;
+    }
+    if (!b.want_grad) return;
+    if (info) {
+        if (tid <= L) b.grad[(size_t)e * (L + 1) + tid] = 0.0;
+        return;
+    }
+
+    // ---- gradient: W = a a' - K~^-1 contracted with K and dK/drho ----------------------------------
+    if (active && ti == tN) {   // border row holds a = K~^-1 r
+        double vals[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double x = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (r == rN) x = A[r][c];
+            vals[c] = (tj * 8 + c < N) ? x : 0.0;
+        }
+        store8(abuf, tj, T, vals);
+    }
+    __syncthreads();
+
+    if (b.dump_kinv && active) {   // K~^-1 = -(swept matrix); written once per gpcc call (postb / pred), not in the fit loop
+        double* out = b.dump_kinv + (size_t)e * N * N;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int i = ti * 8 + r, j = tj * 8 + c;
+                if (i < N && j < N && j <= i) { out[(size_t)j * N + i] = -A[r][c]; out[(size_t)i * N + j] = -A[r][c]; }
+            }
+    }
+    if (b.dump_a) for (int i = tid; i < N; i += nthreads) b.dump_a[(size_t)e * N + i] = abuf[cidx(i, T)];
+
+    double rows[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) rows[r] = 0.0;
+    double es = 0.0;
+    const bool diag_tile = (ti == tj);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double tc[4], ac[4], wc[4], cols[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int cj = cidx(tj * 8 + half * 4 + cc, T);
+            tc[cc] = tsh[cj]; ac[cc] = av[cj]; wc[cc] = abuf[cj]; cols[cc] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int ci = cidx(ti * 8 + r, T);
+            const double tr = tsh[ci], ar = av[ci], wr = abuf[ci];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
+                const double W = fma(wr, wc[cc], A[r][c]);       // a_i a_j - (K~^-1)_ij
+                double kv, dkv;
+                kern_value_drho<KID>(tr - tc[cc], kp, kv, dkv);
+                const double aa = ar * ac[cc];                   // 0 on padding / border rows
+                double ct = W * (aa * kv);
+                double et = W * (aa * dkv);
+                if (diag_tile) {
+                    if (r == c) { rows[r] += ct; ct = 0.0; et = 0.0; }   // diagonal counted once, dk(0)=0
+                    else if (r < c) { ct = 0.0; et = 0.0; }              // upper part of the tile is unused
+                }
+                rows[r] += ct;
+                cols[cc] += ct;
+                es += et;
+            }
+        }
+        if (active) {
+            if (!diag_tile) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) part[(tj * T + ti) * 8 + half * 4 + cc] = cols[cc];
+            } else {
+                // fold the column sums of the strictly-lower part into the same slot as the row sums
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) if (r == half * 4 + cc) rows[r] += cols[cc];
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[(ti * T + tj) * 8 + r] = rows[r];
+    }
+    es = block_sum(active ? es : 0.0, red, tid, nthreads);   // (contains the __syncthreads that orders `part`)
+
+    // s_i = sum_j W_ij K_ij (full row);  dlogL/dalpha_p = (1/alpha_p) sum_{i in band p} s_i
+    double* srow = cbuf;   // natural layout, reuse
+    for (int i = tid; i < N; i += nthreads) {
+        const double* pp = part + (size_t)(i >> 3) * T * 8 + (i & 7);
+        double s = 0.0;
+        for (int src = 0; src < T; ++src) s += pp[src * 8];
+        srow[i] = s;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = (nthreads + 31) >> 5;
+    for (int pb = warp; pb < L; pb += nwarps) {
+        double s = 0.0;
+        for (int i = p.band_start[pb] + lane; i < p.band_start[pb + 1]; i += 32) s += srow[i];
+        s = warp_sum(s);
+        if (lane == 0) b.grad[(size_t)e * (L + 1) + pb] = s / b.alpha[(size_t)e * L + pb];
+    }
+    if (tid == 0) b.grad[(size_t)e * (L + 1) + L] = es;   // 0.5 * sum_full = sum over the strict lower triangle
+}
+
+size_t smem_bytes(int T, int want_grad) {
+    const int Np = T * TS;
+    size_t doubles = (size_t)Np * 8 + 4 + 64 + (want_grad ? (size_t)T * T * 8 : 0);
+    return doubles * sizeof(double) + (size_t)Np * sizeof(int) + 16;
+}
+
+template <int KID>
+cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStream_t s) {
+    const int ntiles = T * (T + 1) / 2;
+    const int threads = (ntiles + 31) / 32 * 32;
+    const size_t sm = smem_bytes(T, b.want_grad);
+    if (threads <= 128) {
+        auto kfn = small_sweep_kernel<KID, 128, 2>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
+        kfn<<<b.M, threads, sm, s>>>(p, b, T);
+    } else if (threads <= 224) {
+        auto kfn = small_sweep_kernel<KID, 224, 1>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(20, 1));
+        kfn<<<b.M, threads, sm, s>>>(p, b, T);
+    } else {
+        auto kfn = small_sweep_kernel<KID, 352, 1>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(SMALL_MAX_T, 1));
+        kfn<<<b.M, threads, sm, s>>>(p, b, T);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t small_sweep_init() { return cudaSuccess; }
+
+cudaError_t small_sweep_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t s) {
+    const int T = (p.N + 1 + TS - 1) / TS;
+    switch (p.kernel_id) {
+        case K_OU:  return launch_kid<K_OU>(p, b, T, s);
+        case K_RBF: return launch_kid<K_RBF>(p, b, T, s);
+        case K_M32: return launch_kid<K_M32>(p, b, T, s);
+        case K_M52: return launch_kid<K_M52>(p, b, T, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace gpcc
