@@ -24,6 +24,7 @@
 #include "kernfun.cuh"
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 namespace gpcc {
 
@@ -79,15 +80,21 @@ __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, in
                                            double* cbuf, double* pbuf, double* piv, bool active) {
     const double* cb = cbuf + (k & 1) * Np;
     double cr[8], v[8];
-    load8(cb, ti, T, cr);
     load8(cb, tj, T, v);
     const double pr = pbuf[k & 1];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] *= pr;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int part = 0; part < 4; ++part) {   // rows two at a time: keeps only a pair of broadcast values live
+        const double2 x = *reinterpret_cast<const double2*>(cb + part * 2 * T + 2 * ti);
+        cr[2 * part] = x.x;
+        cr[2 * part + 1] = x.y;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) A[r][c] = fma(-cr[r], v[c], A[r][c]);
+        for (int c = 0; c < 8; ++c) {
+            A[2 * part][c] = fma(-x.x, v[c], A[2 * part][c]);
+            A[2 * part + 1][c] = fma(-x.y, v[c], A[2 * part + 1][c]);
+        }
+    }
     if (tj == tk) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) A[r][KK] = cr[r] * pr;
@@ -365,9 +372,20 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
     const int ntiles = T * (T + 1) / 2;
     const int threads = (ntiles + 31) / 32 * 32;
     const size_t sm = smem_bytes(T, b.want_grad);
+    static const int variant = getenv("GPCC_SMALL_VARIANT") ? atoi(getenv("GPCC_SMALL_VARIANT")) : 1;
     if (threads <= 128) {
-        auto kfn = small_sweep_kernel<KID, 128, 2>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
+        if (variant == 2) {
+            auto kfn = small_sweep_kernel<KID, 128, 3>;
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
+            kfn<<<b.M, threads, sm, s>>>(p, b, T);
+        } else {
+            auto kfn = small_sweep_kernel<KID, 128, 2>;
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
+            kfn<<<b.M, threads, sm, s>>>(p, b, T);
+        }
+    } else if (threads <= 192 && variant == 1) {
+        auto kfn = small_sweep_kernel<KID, 192, 2>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
         kfn<<<b.M, threads, sm, s>>>(p, b, T);
     } else if (threads <= 224) {
         auto kfn = small_sweep_kernel<KID, 224, 1>;
