@@ -1,8 +1,7 @@
 // C ABI of libgpcc_b200.so (include/gpcc_b200.h): contexts, problems, batched evaluation, the
 // host-driven batched L-BFGS fit, the grid posterior, postb and predictions.
 // There is no CPU fallback anywhere in this file: every likelihood value comes from a CUDA kernel.
-#include "../../include/gpcc_b200.h"
-#include "gpcc_internal.h"
+#include "state.h"
 #include "lbfgs.h"
 
 #include <algorithm>
@@ -17,83 +16,14 @@
 
 using namespace gpcc;
 
-namespace {
-
-thread_local std::string g_last_error;
-
+namespace gpcc {
+namespace { thread_local std::string g_last_error; }
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
-#define CUDA_TRY(expr)                                                                            \
-    do {                                                                                          \
-        cudaError_t _e = (expr);                                                                  \
-        if (_e != cudaSuccess) {                                                                  \
-            cudaGetLastError();                                                                   \
-            return fail(1000 + (int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
-        }                                                                                         \
-    } while (0)
-
-template <class T>
-struct DevBuf {   // growable device buffer + pinned host mirror
-    T* d = nullptr;
-    T* h = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        release();
-        size_t c = std::max<size_t>(n, 1024);
-        c = c + c / 2;
-        cudaError_t e = cudaMalloc(&d, c * sizeof(T));
-        if (e != cudaSuccess) return e;
-        e = cudaMallocHost(&h, c * sizeof(T));
-        if (e != cudaSuccess) return e;
-        cap = c;
-        return cudaSuccess;
-    }
-    void release() {
-        if (d) cudaFree(d);
-        if (h) cudaFreeHost(h);
-        d = nullptr; h = nullptr; cap = 0;
-    }
-};
-
-struct DeviceState {
-    int dev = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf<double> delays, alpha, rho, ll, grad;
-    DevBuf<int> info;
-    LargeWorkspace large;     // tiled large-N path (large_path.cu)
-    // per-call statistics (profiling)
-    double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
-    long long launches = 0, evals = 0, evals_grad = 0;
-    std::string err;
-    int err_code = 0;
-};
-
-}  // namespace
-
-struct gpcc_ctx {
-    std::vector<DeviceState> ds;
-    bool profiling = false;
-    gpcc_stats stats{};
-    NcclBridge* nccl = nullptr;
-};
-
-struct gpcc_problem {
-    gpcc_ctx* ctx = nullptr;
-    int L = 0, N = 0, kernel_id = 0;
-    std::vector<int> n_per_band, band, band_start;
-    std::vector<double> t, y, sigma, mub, Sigmab, resid, s2, sigb;
-    struct PerDev {
-        double *t = nullptr, *resid = nullptr, *s2 = nullptr, *sigb = nullptr;
-        int* band = nullptr;
-        DevProblem dp;
-    };
-    std::vector<PerDev> pd;
-    bool small_path = true;
-};
+const std::string& last_error() { return g_last_error; }
+}  // namespace gpcc
 
 namespace {
 
@@ -121,8 +51,9 @@ int check_options(const gpcc_fit_options* o) {
 
 // Evaluate `M` (delay, alpha, rho) triples that already sit in the pinned host mirrors of `s`.
 // Results land in s.ll.h / s.grad.h / s.info.h.
-int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv = nullptr,
-                       double* dump_a = nullptr) {
+}  // namespace
+int gpcc::evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv, double* dump_a,
+                             int mode_postb) {
     DeviceState& s = p->ctx->ds[di];
     const int L = p->L;
     CUDA_TRY(cudaSetDevice(s.dev));
@@ -131,7 +62,7 @@ int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* du
     CUDA_TRY(cudaMemcpyAsync(s.rho.d, s.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     EvalBatch b;
     b.M = M; b.delays = s.delays.d; b.alpha = s.alpha.d; b.rho = s.rho.d; b.want_grad = want_grad;
-    b.ll = s.ll.d; b.grad = s.grad.d; b.info = s.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a;
+    b.ll = s.ll.d; b.grad = s.grad.d; b.info = s.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a; b.mode_postb = mode_postb;
     const bool prof = p->ctx->profiling;
     if (p->small_path) {
         if (prof) CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
@@ -160,7 +91,7 @@ int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* du
     return 0;
 }
 
-int reserve_eval(gpcc_problem* p, int di, size_t M) {
+int gpcc::reserve_eval(gpcc_problem* p, int di, size_t M) {
     DeviceState& s = p->ctx->ds[di];
     const int L = p->L;
     CUDA_TRY(cudaSetDevice(s.dev));
@@ -173,6 +104,7 @@ int reserve_eval(gpcc_problem* p, int di, size_t M) {
     return 0;
 }
 
+namespace {
 void reset_stats(gpcc_ctx* ctx) {
     for (auto& s : ctx->ds) {
         s.ms_eval = s.ms_assembly = s.ms_factor = s.ms_gradreduce = 0;
@@ -318,7 +250,7 @@ int for_each_device(gpcc_ctx* ctx, F fn) {
     std::vector<std::string> errs(nd);
     std::vector<std::thread> th;
     for (int di = 0; di < nd; ++di)
-        th.emplace_back([&, di]() { rcs[di] = fn(di); errs[di] = g_last_error; });
+        th.emplace_back([&, di]() { rcs[di] = fn(di); errs[di] = gpcc::last_error(); });
     for (auto& t : th) t.join();
     for (int di = 0; di < nd; ++di)
         if (rcs[di]) return fail(rcs[di], "device " + std::to_string(ctx->ds[di].dev) + ": " + errs[di]);
@@ -340,7 +272,7 @@ int fit_all(gpcc_problem* p, int M, const double* delays, int P, const double* t
 extern "C" {
 
 int gpcc_version(void) { return 100; }
-const char* gpcc_last_error(void) { return g_last_error.c_str(); }
+const char* gpcc_last_error(void) { return gpcc::last_error().c_str(); }
 
 int gpcc_fit_options_default(gpcc_fit_options* o) {
     if (!o) return fail(-1, "options pointer is NULL");
@@ -470,16 +402,18 @@ int gpcc_problem_create(gpcc_ctx* ctx, int L, const int* n_per_band, const doubl
         CUDA_TRY(cudaSetDevice(ctx->ds[di].dev));
         CUDA_TRY(cudaMalloc(&d.t, N * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.resid, N * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.y, N * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.s2, N * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.sigb, N * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.band, N * sizeof(int)));
         CUDA_TRY(cudaMemcpy(d.t, p->t.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.resid, p->resid.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.y, p->y.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.s2, p->s2.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.sigb, p->sigb.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.band, p->band.data(), N * sizeof(int), cudaMemcpyHostToDevice));
         d.dp.N = N; d.dp.L = L; d.dp.kernel_id = kernel_id;
-        d.dp.t = d.t; d.dp.resid = d.resid; d.dp.s2 = d.s2; d.dp.sigb = d.sigb; d.dp.band = d.band;
+        d.dp.t = d.t; d.dp.resid = d.resid; d.dp.y = d.y; d.dp.s2 = d.s2; d.dp.sigb = d.sigb; d.dp.band = d.band;
         for (int l = 0; l <= L; ++l) d.dp.band_start[l] = p->band_start[l];
     }
     *out = p;
@@ -491,7 +425,7 @@ int gpcc_problem_destroy(gpcc_problem* p) {
     for (size_t di = 0; di < p->pd.size(); ++di) {
         cudaSetDevice(p->ctx->ds[di].dev);
         auto& d = p->pd[di];
-        cudaFree(d.t); cudaFree(d.resid); cudaFree(d.s2); cudaFree(d.sigb); cudaFree(d.band);
+        cudaFree(d.t); cudaFree(d.resid); cudaFree(d.y); cudaFree(d.s2); cudaFree(d.sigb); cudaFree(d.band);
     }
     delete p;
     return 0;

@@ -13,6 +13,7 @@ struct DevProblem {
     int kernel_id = 0;
     const double* t = nullptr;      // [N] observation times, bands concatenated
     const double* resid = nullptr;  // [N] Y - bbar            (gpccfixdelay_marginaliseb.jl:85,98)
+    const double* y = nullptr;      // [N] Y                   (:85; right-hand side of the postb solve, :250)
     const double* s2 = nullptr;     // [N] sigma^2  (Sobs)     (:89)
     const double* sigb = nullptr;   // [N] Sigma_b[band(i)]    (:94-96, B = Q Sigma_b Q')
     const int* band = nullptr;      // [N] band index of point i
@@ -31,6 +32,7 @@ struct EvalBatch {
     int* info = nullptr;             // [M]
     double* dump_kinv = nullptr;     // optional [M][N*N] dense column-major K~^-1 (both triangles)
     double* dump_a = nullptr;        // optional [M][N]   a = K~^-1 (Y - bbar)
+    int mode_postb = 0;              // 1: factor Sobs + K WITHOUT B and solve against Y (postb, :248-250)
 };
 
 // ---- small-N path: fused register-resident symmetric sweep (small_sweep.cu) -------------------

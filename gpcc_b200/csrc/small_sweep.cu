@@ -168,9 +168,9 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
             const int bi = p.band[i];
             tsh[ci] = p.t[i] - b.delays[(size_t)e * L + bi];   // delayedCovariance.jl:27 (x - delays[l])
             av[ci] = b.alpha[(size_t)e * L + bi];
-            sbv[ci] = p.sigb[i];
+            sbv[ci] = b.mode_postb ? 0.0 : p.sigb[i];
             dadd[ci] = p.s2[i];
-            abuf[ci] = p.resid[i];
+            abuf[ci] = b.mode_postb ? p.y[i] : p.resid[i];
             bandv[i] = bi;
         } else {
             tsh[ci] = 0.0; av[ci] = 0.0; sbv[ci] = 0.0; dadd[ci] = 0.0; abuf[ci] = 0.0;

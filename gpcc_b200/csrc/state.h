@@ -1,0 +1,88 @@
+// Shared host-side state of libgpcc_b200.so (contexts, problems, per-device staging).
+#pragma once
+#include "../../include/gpcc_b200.h"
+#include "gpcc_internal.h"
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace gpcc {
+
+int fail(int code, const std::string& msg);
+const std::string& last_error();
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            cudaGetLastError();                                                                   \
+            return gpcc::fail(1000 + (int)_e, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                         \
+    } while (0)
+
+template <class T>
+struct DevBuf {   // growable device buffer + pinned host mirror
+    T* d = nullptr;
+    T* h = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t c = std::max<size_t>(n, 1024);
+        c = c + c / 2;
+        cudaError_t e = cudaMalloc(&d, c * sizeof(T));
+        if (e != cudaSuccess) return e;
+        e = cudaMallocHost(&h, c * sizeof(T));
+        if (e != cudaSuccess) return e;
+        cap = c;
+        return cudaSuccess;
+    }
+    void release() {
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        d = nullptr; h = nullptr; cap = 0;
+    }
+};
+
+struct DeviceState {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<double> delays, alpha, rho, ll, grad;
+    DevBuf<int> info;
+    LargeWorkspace large;     // tiled large-N path (large_path.cu)
+    // per-call statistics (profiling)
+    double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
+    long long launches = 0, evals = 0, evals_grad = 0;
+};
+
+}  // namespace gpcc
+
+struct gpcc_ctx {
+    std::vector<gpcc::DeviceState> ds;
+    bool profiling = false;
+    gpcc_stats stats{};
+    gpcc::NcclBridge* nccl = nullptr;
+};
+
+struct gpcc_problem {
+    gpcc_ctx* ctx = nullptr;
+    int L = 0, N = 0, kernel_id = 0;
+    std::vector<int> n_per_band, band, band_start;
+    std::vector<double> t, y, sigma, mub, Sigmab, resid, s2, sigb;
+    struct PerDev {
+        double *t = nullptr, *resid = nullptr, *y = nullptr, *s2 = nullptr, *sigb = nullptr;
+        int* band = nullptr;
+        gpcc::DevProblem dp;
+    };
+    std::vector<PerDev> pd;
+    bool small_path = true;
+};
+
+namespace gpcc {
+// Evaluate M (delay, alpha, rho) triples already staged in the pinned mirrors of device `di`;
+// results land in ds[di].ll.h / grad.h / info.h.  Optionally dumps K~^-1 (dense) and a = K~^-1 r.
+int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv = nullptr,
+                       double* dump_a = nullptr, int mode_postb = 0);
+int reserve_eval(gpcc_problem* p, int di, size_t M);
+}  // namespace gpcc

@@ -1,0 +1,211 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the oracle
+and the committed golden fixtures.  Tolerances are the ones BASELINE.json's north_star states:
+  fixed-hyperparameter log-likelihood   1e-10 relative
+  optimised loglikel                    1e-6 absolute (vs the oracle's L-BFGS optimum; Nelder-Mead stops earlier)
+  posterior delay probabilities         1e-4 absolute
+  pred means / standard deviations      1e-8 relative
+"""
+import numpy as np
+import pytest
+
+import gpcc_b200
+import oracle
+from conftest import load_golden
+from gpcc_b200 import Problem
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-10
+GRAD_RTOL = 1e-8          # gradient is not toleranced by north_star; it only steers the optimiser
+FIT_ATOL = 1e-6
+POST_ATOL = 1e-4
+PRED_RTOL = 1e-8
+
+GOLDEN_LL = [f"loglik_{b}_{k}" for b in ("2band", "3band") for k in ("OU", "rbf", "matern32", "matern52")] + \
+            ["loglik_3x64_matern52", "loglik_ragged_OU", "loglik_single_band_rbf"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_LL)
+def test_loglik_and_gradient_match_golden(ctx, name):
+    g = load_golden(name)
+    p = Problem(g["tb"], g["yb"], g["sb"], g["kernel"], ctx)
+    assert np.allclose(p.mub, g["mub"], rtol=1e-14) and np.allclose(p.Sigmab, g["Sigmab"], rtol=1e-13)
+    ll, grad, info = p.loglik_batch(g["delays"], g["alpha"], g["rho"], want_grad=True)
+    assert np.all(info == 0)
+    assert np.max(np.abs(ll - g["loglik"]) / np.abs(g["loglik"])) < LL_RTOL
+    scale = np.max(np.abs(g["grad"]), axis=1, keepdims=True)
+    assert np.max(np.abs(grad - g["grad"]) / scale) < GRAD_RTOL
+    ll2, info2 = p.loglik_batch(g["delays"], g["alpha"], g["rho"])            # without gradient: identical values
+    assert np.array_equal(ll2, ll)
+
+
+def test_loglik_matches_oracle_on_fresh_inputs(ctx):
+    t, y, s, d = oracle.simulatedata(sigma=0.5, seed=7)[:4]
+    for kernel in oracle.KERNELS:
+        op, p = oracle.Problem(t, y, s, kernel), Problem(t, y, s, kernel, ctx)
+        rg = np.random.default_rng(3)
+        M = 40
+        delays = np.zeros((M, 3)); delays[:, 1:] = rg.uniform(-5, 25, (M, 2))
+        alpha, rho = rg.uniform(0.05, 5.0, (M, 3)), np.exp(rg.uniform(np.log(0.1), np.log(300.0), M))
+        ll, grad, info = p.loglik_batch(delays, alpha, rho, want_grad=True)
+        ref = [op.loglik_grad(delays[m], alpha[m], rho[m]) for m in range(M)]
+        rl, rgd = np.array([r[0] for r in ref]), np.array([r[1] for r in ref])
+        assert np.all(info == 0)
+        assert np.max(np.abs(ll - rl) / np.abs(rl)) < LL_RTOL, kernel
+        assert np.max(np.abs(grad - rgd) / np.max(np.abs(rgd), axis=1, keepdims=True)) < GRAD_RTOL, kernel
+
+
+def test_theta_space_gradient_chain_rule(ctx):
+    g = load_golden("loglik_3band_matern32")
+    op, p = oracle.Problem(g["tb"], g["yb"], g["sb"], "matern32"), Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    rg = np.random.default_rng(5)
+    theta = rg.normal(0.0, 1.5, (16, 4))
+    delays = np.tile([0.0, 2.0, 4.0], (16, 1))
+    ll, grad, info = p.loglik_theta_batch(delays, theta, 0.1, 300.0, want_grad=True)
+    for m in range(16):
+        rl, rgd = op.objective_grad_theta(theta[m], delays[m], 0.1, 300.0)
+        assert abs(ll[m] - rl) / abs(rl) < LL_RTOL
+        assert np.max(np.abs(grad[m] - rgd)) / np.max(np.abs(rgd)) < GRAD_RTOL
+
+
+def test_determinism_and_batch_independence(ctx):
+    g = load_golden("loglik_3band_OU")
+    p = Problem(g["tb"], g["yb"], g["sb"], "OU", ctx)
+    a = p.loglik_batch(g["delays"], g["alpha"], g["rho"], want_grad=True)
+    b = p.loglik_batch(g["delays"], g["alpha"], g["rho"], want_grad=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])             # bitwise reproducible
+    perm = np.random.default_rng(0).permutation(len(g["rho"]))
+    c = p.loglik_batch(g["delays"][perm], g["alpha"][perm], g["rho"][perm], want_grad=True)
+    assert np.array_equal(c[0], a[0][perm]) and np.array_equal(c[1], a[1][perm])
+    big = p.loglik_batch(np.tile(g["delays"], (50, 1)), np.tile(g["alpha"], (50, 1)), np.tile(g["rho"], 50))
+    assert np.array_equal(big[0], np.tile(a[0], 50))                             # 1200 CTAs, several waves
+
+
+def test_not_positive_definite_and_invalid_hyperparameters(ctx):
+    # duplicated time stamps with zero noise: K + Sobs + B is singular -> LAPACK-style info > 0, loglik = -Inf
+    t = [np.array([1.0, 1.0, 2.0, 3.0]), np.array([1.5, 2.5, 2.5])]
+    y = [np.array([1.0, 2.0, 1.5, 0.5]), np.array([3.0, 2.0, 2.5])]
+    s = [np.zeros(4), np.zeros(3)]
+    p = Problem(t, y, s, "rbf", ctx)
+    ll, grad, info = p.loglik_batch([[0.0, 0.0]], [[1.0, 1.0]], [1.0], want_grad=True)
+    assert info[0] > 0 and ll[0] == -np.inf and np.all(grad == 0.0)
+    # scale <= 0 / rho <= 0 are errors in delayedCovariance.jl:3-7 -> info -1, -Inf, nothing sent to the device
+    ll, info = p.loglik_batch([[0.0, 0.0]] * 3, [[1.0, -1.0], [1.0, 1.0], [np.nan, 1.0]], [1.0, 0.0, 1.0])
+    assert np.all(info == -1) and np.all(ll == -np.inf)
+    with pytest.raises(gpcc_b200.GpccError):
+        Problem([np.array([1.0])], [np.array([1.0])], [np.array([0.1])], "OU", ctx)    # var of one point is undefined
+    with pytest.raises(gpcc_b200.GpccError):
+        Problem(t, y, s, "cosine", ctx)
+
+
+def test_empty_batch_and_single_candidate(ctx):
+    g = load_golden("loglik_2band_rbf")
+    p = Problem(g["tb"], g["yb"], g["sb"], "rbf", ctx)
+    ll, info = p.loglik_batch(np.zeros((0, 2)), np.zeros((0, 2)), np.zeros(0))
+    assert ll.shape == (0,)
+    ll, info = p.loglik_batch(g["delays"][:1], g["alpha"][:1], g["rho"][:1])
+    assert abs(ll[0] - g["loglik"][0]) / abs(g["loglik"][0]) < LL_RTOL
+
+
+# ---- fit, posterior (configs 1-3) -------------------------------------------------------------------------
+def test_cfg1_single_fit_matches_oracle(ctx, capsys):
+    g = load_golden("fit_cfg1_cfg2")
+    loglikel, pred, (alpha, postb, rho) = gpcc_b200.gpcc(g["tb"], g["yb"], g["sb"], kernel=gpcc_b200.matern32,
+                                                        delays=g["truedelays"], iterations=1000, rhomax=300,
+                                                        theta0=g["theta0"], ctx=ctx)
+    out = capsys.readouterr().out
+    assert "Running with random seed 1" in out and "Overall minimum is" in out        # util.jl:1-11, :228
+    assert abs(loglikel - float(g["loglikel"])) < FIT_ATOL
+    assert loglikel >= float(g["loglikel_nm"]) - FIT_ATOL          # never worse than the reference's Nelder-Mead
+    assert np.allclose(alpha, g["alpha"], rtol=1e-4) and rho == pytest.approx(float(g["rho"]), rel=1e-4)
+    # postb (:248-252) evaluated at the oracle's optimum so that only the linear algebra is compared
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    mu, S = p.postb(g["truedelays"], g["alpha"], float(g["rho"]))
+    assert np.allclose(mu, g["postb_mu"], rtol=PRED_RTOL) and np.allclose(S, g["postb_Sigma"], rtol=PRED_RTOL)
+    assert np.array_equal(S, S.T) and isinstance(postb, gpcc_b200.MvNormal)
+    # pred(t::Vector) (:293-307)
+    m_, sd_, _, _ = p.predict(g["truedelays"], g["alpha"], float(g["rho"]), [g["ttest"]] * 2)
+    nt = len(g["ttest"])
+    assert np.max(np.abs(m_.reshape(2, nt) - g["pred_mu"]) / np.abs(g["pred_mu"])) < PRED_RTOL
+    assert np.max(np.abs(sd_.reshape(2, nt) - g["pred_sd"]) / g["pred_sd"]) < PRED_RTOL
+    mu_b, sd_b = pred(g["ttest"])
+    assert len(mu_b) == 2 and mu_b[0].shape == (nt,) and np.allclose(mu_b[1], g["pred_mu"][1], rtol=1e-4)
+    # pred(t::Vector{Vector}) -> (mu, Sigma) (:259-289), ragged test sets
+    mf, _, Sf, _ = p.predict(g["truedelays"], g["alpha"], float(g["rho"]), [g["ttest"][:7], g["ttest"][5:9]], full_cov=True)
+    assert np.max(np.abs(mf - g["predfull_mu"]) / np.abs(g["predfull_mu"])) < PRED_RTOL
+    assert np.max(np.abs(Sf - g["predfull_Sigma"])) / np.max(np.abs(g["predfull_Sigma"])) < PRED_RTOL
+    assert np.array_equal(Sf, Sf.T)
+    # pred(ttest, ytest, sigmatest) (:311-343), the README's numbers
+    tl, info = p.predict_loglik(g["truedelays"], g["alpha"], float(g["rho"]), [[9.0, 10.0, 11.0], [9.0, 10.0, 11.0]],
+                                [[6.34, 5.49, 5.38], [13.08, 12.37, 15.69]], [[0.34, 0.42, 0.2], [0.87, 0.8, 0.66]])
+    assert info == 0 and abs(tl - float(g["test_loglik"])) / abs(float(g["test_loglik"])) < PRED_RTOL
+
+
+def test_cfg2_grid_posterior_matches_oracle(ctx):
+    g = load_golden("fit_cfg1_cfg2")
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    delays = np.stack([np.zeros_like(g["cands"]), g["cands"]], 1)
+    res = p.grid_posterior(delays, g["theta0"], iterations=1000, rhomin=0.1, rhomax=300.0)
+    gap = np.abs(res["loglikel"] - g["ll_grid"])
+    carries_mass = g["post_flat"] > 1e-12
+    # same basin wherever the candidate carries posterior mass (SURVEY.md section 7 "hard parts")
+    assert np.max(gap[carries_mass]) < FIT_ATOL, (np.max(gap), np.argmax(gap))
+    assert np.sum(gap > FIT_ATOL) <= 2, "basin mismatches: %d" % np.sum(gap > FIT_ATOL)
+    assert np.all(res["loglikel"] >= g["ll_grid_nm"] - 1e-5)      # at least as good as the reference optimiser everywhere
+    assert np.max(np.abs(res["posterior"] - g["post_flat"])) < POST_ATOL
+    assert np.max(np.abs(res["posterior"] - oracle.getprobabilities(g["ll_grid_nm"]))) < POST_ATOL
+    assert res["posterior"].sum() == pytest.approx(1.0, abs=1e-12)
+    prior = gpcc_b200.uniformpriordelay(L=1e44, z=0.0)
+    res2 = p.grid_posterior(delays, g["theta0"], iterations=1000, rhomin=0.1, rhomax=300.0, logprior=prior.logpdf(g["cands"]))
+    assert np.max(np.abs(res2["posterior"] - g["post_prior"])) < POST_ATOL
+    # getprobabilities on the device, shape preserving, -Inf -> 0 (getprobabilities.jl:1-20)
+    ll2 = g["ll_grid"][:100].reshape(10, 10).copy()
+    ll2[3, 4] = -np.inf
+    pp = gpcc_b200.getprobabilities(ll2, ctx=ctx)
+    assert pp.shape == (10, 10) and pp[3, 4] == 0.0 and np.allclose(pp, oracle.getprobabilities(ll2), rtol=1e-12, atol=1e-300)
+
+
+def test_cfg3_subgrid_three_bands(ctx):
+    g = load_golden("fit_cfg3_subgrid")
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    res = p.grid_posterior(g["delays"], g["theta0"], iterations=1000, rhomin=0.1, rhomax=300.0)
+    gap = np.abs(res["loglikel"] - g["ll"])
+    assert np.max(gap[g["post"] > 1e-12]) < FIT_ATOL
+    assert np.max(np.abs(res["posterior"] - g["post"])) < POST_ATOL
+    assert np.allclose(g["delays"][np.argmax(res["posterior"])], [0.0, 2.0, 4.0])
+    # basin report: candidates whose optimum differs from the oracle's L-BFGS by more than 1e-6 carry no mass
+    assert np.all(g["post"][gap > FIT_ATOL] < 1e-12)
+
+
+def test_full_size_cfg3_grid_properties(ctx):
+    """BASELINE config 3 at full size (101 x 101 = 10 201 candidates): size-independent properties."""
+    t, y, s, d = oracle.simulatethreelightcurves()
+    p = Problem(t, y, s, "matern32", ctx)
+    c = np.arange(0.0, 20.0001, 0.2)
+    delays = np.array([[0.0, a, b] for b in c for a in c])            # d1 fastest (README.md:231-235)
+    theta0 = gpcc_b200.initial_solutions(y, 1, 1, 5, 0.1, 300.0)[0][0]
+    res = p.grid_posterior(delays, theta0, iterations=1000, rhomin=0.1, rhomax=300.0)
+    post = res["posterior"].reshape(101, 101, order="F")             # reshape(posterior, n, n) in Julia
+    assert post.sum() == pytest.approx(1.0, abs=1e-10) and np.all(post >= 0)
+    i, j = np.unravel_index(np.argmax(post), post.shape)
+    assert abs(c[i] - 2.0) <= 0.4 and abs(c[j] - 4.0) <= 0.4          # truth (2, 4)
+    # the optimum can only improve on the best screening point, and re-evaluating theta-hat reproduces loglikel
+    ll_chk, _ = p.loglik_batch(delays[::97], res["alpha"][::97], res["rho"][::97])
+    assert np.allclose(ll_chk, res["loglikel"][::97], rtol=1e-12)
+    scr = np.max(np.stack([p.loglik_theta_batch(delays[::97], np.tile(th, (len(delays[::97]), 1)), 0.1, 300.0)[0]
+                           for th in theta0]), axis=0)
+    assert np.all(res["loglikel"][::97] >= scr - 1e-9)
+    assert np.all(res["info"] >= 0)
+
+
+def test_restarts_and_per_candidate_starts(ctx):
+    g = load_golden("fit_cfg1_cfg2")
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    th, _ = gpcc_b200.initial_solutions(g["yb"], seed=3, numberofrestarts=3, initialrandom=4, rhomin=0.1, rhomax=300.0)
+    res = p.fit_batch(np.tile(g["truedelays"], (3, 1)), th, iterations=1000, rhomin=0.1, rhomax=300.0)   # [M][P][L+1]
+    assert np.max(res["loglikel"]) >= float(g["loglikel"]) - 1e-6
+    ll, _, _ = gpcc_b200.gpcc(g["tb"], g["yb"], g["sb"], kernel="matern32", delays=g["truedelays"], iterations=1000,
+                              rhomax=300, seed=3, numberofrestarts=3, initialrandom=4, ctx=ctx, verbose=False)
+    assert ll == pytest.approx(np.max(res["loglikel"]), abs=1e-9)
+    capped = p.fit_batch(g["truedelays"][None], g["theta0"], iterations=2, rhomin=0.1, rhomax=300.0)
+    assert capped["info"][0] == 1 and capped["iters"][0] == 2 and capped["loglikel"][0] < float(g["loglikel"])

@@ -1,0 +1,197 @@
+"""CPU tests of the oracle (the reference restatement) against first principles and the golden fixtures.
+
+The reference has no tests or golden vectors (test/runtests.jl:4-6), so the oracle is pinned by:
+ 50-digit mpmath evaluation, finite differences, the Woodbury identity (independent route to the
+ marginalised likelihood and to postb), and the element-wise statement of K+Sobs+B in
+ src/gpccfixdelay_verifications.jl:130-150.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_golden
+
+KERNELS = list(oracle.KERNELS)
+
+
+@pytest.fixture(scope="module")
+def data3():
+    return oracle.simulatethreelightcurves()
+
+
+def test_simulator_shape(data3):
+    t, y, s, d = data3
+    assert [len(a) for a in t] == [60, 50, 40]                      # simulatedata.jl:119
+    assert np.all((t[1] <= 8.0) | (t[1] >= 12.0))                    # gap in band 2 (:121)
+    assert np.allclose(d, [0.0, 2.0, 4.0]) and all(np.all(a == 0.75) for a in s)
+    t2, y2, s2, d2 = oracle.simulatetwolightcurves()
+    assert len(t2) == 2 and np.array_equal(t2[0], t[0]) and np.array_equal(y2[1], y[1])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_kernels_unit_diagonal_and_formulas(kernel):
+    assert oracle.kernel_value(kernel, 0.0, 2.3) == 1.0
+    d, rho = 1.7, 2.3
+    r = abs(d)
+    expect = {"OU": np.exp(-r / rho), "rbf": np.exp(-0.5 * d * d / (2 * rho)),                       # util.jl:15-28
+              "matern32": (1 + np.sqrt(3) * r / rho) * np.exp(-np.sqrt(3) * r / rho),               # :32-40
+              "matern52": (1 + np.sqrt(5) * r / rho + 5 * r * r / (3 * rho * rho)) * np.exp(-np.sqrt(5) * r / rho)}[kernel]
+    assert oracle.kernel_value(kernel, d, rho) == pytest.approx(expect, rel=1e-15)
+    assert oracle.kernel_value(kernel, -d, rho) == oracle.kernel_value(kernel, d, rho)
+    h = 1e-6
+    fd = (oracle.kernel_value(kernel, d, rho + h) - oracle.kernel_value(kernel, d, rho - h)) / (2 * h)
+    assert oracle.kernel_drho(kernel, d, rho) == pytest.approx(fd, rel=1e-8)
+
+
+def test_delayed_covariance_elementwise_and_errors(data3):
+    t, y, s, d = data3
+    alpha, rho = np.array([1.1, 1.6, 2.2]), 2.5
+    K = oracle.delayed_covariance("matern32", alpha, d, rho, t)
+    assert np.array_equal(K, K.T)                                    # bit-exact symmetry
+    off = np.concatenate([[0], np.cumsum([len(a) for a in t])])
+    for (l, i, m, j) in [(0, 3, 0, 3), (0, 5, 2, 7), (1, 49, 2, 0), (2, 39, 1, 11)]:
+        e = alpha[l] * alpha[m] * oracle.kernel_value("matern32", (t[l][i] - d[l]) - (t[m][j] - d[m]), rho)
+        assert K[off[l] + i, off[m] + j] == pytest.approx(e, rel=1e-15)   # delayedCovariance.jl:27
+    Kr = oracle.delayed_covariance("OU", alpha, d, rho, t, [np.array([1.0, 2.0]), np.array([]), np.array([3.0])])
+    assert Kr.shape == (150, 3)
+    with pytest.raises(AssertionError):
+        oracle.delayed_covariance("OU", [1.0, -1.0, 1.0], d, rho, t)     # :3
+    with pytest.raises(ValueError):
+        oracle.delayed_covariance("OU", alpha, d, 0.0, t)                # :5-7
+
+
+def test_full_matrix_matches_verification_statement(data3):
+    """Element-wise K+Sobs+B as written in src/gpccfixdelay_verifications.jl:130-150."""
+    t, y, s, d = data3
+    p = oracle.Problem(t, y, s, "OU")
+    alpha, rho = np.array([0.9, 1.4, 2.1]), 3.0
+    K = p.Ktilde(d, alpha, rho)
+    off = np.concatenate([[0], np.cumsum(p.n)])
+    rg = np.random.default_rng(0)
+    for _ in range(200):
+        l, m = rg.integers(0, 3, 2)
+        i, j = rg.integers(0, p.n[l]), rg.integers(0, p.n[m])
+        e = alpha[l] * alpha[m] * oracle.kernel_value("OU", (t[l][i] - d[l]) - (t[m][j] - d[m]), rho)
+        if l == m:
+            e += p.Sigmab[l]
+            if i == j:
+                e += s[l][i] ** 2
+        assert K[off[l] + i, off[m] + j] == pytest.approx(e, rel=1e-14)
+
+
+@pytest.mark.parametrize("kernel", ["matern32", "OU"])
+def test_loglik_against_mpmath(data3, kernel):
+    import mpmath as mp
+    mp.mp.dps = 50
+    t, y, s, d = data3
+    t, y, s, d = t[:2], y[:2], s[:2], d[:2]
+    p = oracle.Problem(t, y, s, kernel)
+    alpha, rho = np.array([1.2, 1.7]), 3.0
+    K = mp.matrix(p.Ktilde(d, alpha, rho).tolist())
+    r = mp.matrix((p.Y - p.bbar).tolist())
+    Lc = mp.cholesky(K)
+    z = mp.lu_solve(K, r)
+    ll = -0.5 * (p.N * mp.log(2 * mp.pi) + 2 * sum(mp.log(Lc[i, i]) for i in range(p.N)) + sum(r[i] * z[i] for i in range(p.N)))
+    assert abs(p.loglik(d, alpha, rho) - float(ll)) / abs(float(ll)) < 1e-12
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_gradient_against_finite_differences(data3, kernel):
+    t, y, s, d = data3
+    p = oracle.Problem(t, y, s, kernel)
+    alpha, rho = np.array([1.1, 1.6, 2.2]), 2.5
+    ll, g = p.loglik_grad(d, alpha, rho)
+    assert ll == pytest.approx(p.loglik(d, alpha, rho), rel=1e-13)
+    h = 1e-5      # rounding noise of logL (~1e-11 at cond 5e4) / h stays below the tolerance
+    for k in range(4):
+        a2, a1, r2, r1 = alpha.copy(), alpha.copy(), rho, rho
+        if k < 3:
+            a2[k] += h; a1[k] -= h
+        else:
+            r2 += h; r1 -= h
+        fd = (p.loglik(d, a2, r2) - p.loglik(d, a1, r1)) / (2 * h)
+        assert g[k] == pytest.approx(fd, rel=5e-6, abs=5e-6)
+    th = np.array([0.3, -0.2, 0.8, -1.0])
+    ll, gt = p.objective_grad_theta(th, d, 0.1, 300.0)
+    for k in range(4):
+        e = np.zeros(4); e[k] = h
+        fd = (p.objective_theta(th + e, d, 0.1, 300.0) - p.objective_theta(th - e, d, 0.1, 300.0)) / (2 * h)
+        assert gt[k] == pytest.approx(fd, rel=5e-6, abs=5e-6)
+
+
+def test_woodbury_route_to_loglik_and_postb(data3):
+    """logdet(K+S+Q Sb Q') = logdet(K+S) + logdet(Sb) + logdet(Sb^-1 + Q'(K+S)^-1 Q): independent of the objective code."""
+    t, y, s, d = data3
+    p = oracle.Problem(t, y, s, "matern52")
+    alpha, rho = np.array([1.0, 1.5, 2.0]), 3.5
+    KS = oracle.delayed_covariance("matern52", alpha, d, rho, t) + np.diag(p.sobs)
+    Q = (p.band[:, None] == np.arange(3)[None, :]).astype(float)
+    A = np.diag(1 / p.Sigmab) + Q.T @ np.linalg.solve(KS, Q)
+    logdet = np.linalg.slogdet(KS)[1] + np.sum(np.log(p.Sigmab)) + np.linalg.slogdet(A)[1]
+    r = p.Y - p.bbar
+    KSr = np.linalg.solve(KS, r)
+    quad = r @ KSr - (Q.T @ KSr) @ np.linalg.solve(A, Q.T @ KSr)
+    ll = -0.5 * (p.N * np.log(2 * np.pi) + logdet + quad)
+    assert p.loglik(d, alpha, rho) == pytest.approx(ll, rel=1e-11)
+    mu, S = p.postb(d, alpha, rho)
+    # Gaussian conditioning on the marginal covariance gives the same posterior of b
+    Kt = p.Ktilde(d, alpha, rho)
+    mu2 = p.mub + p.Sigmab * (Q.T @ np.linalg.solve(Kt, r))
+    S2 = np.diag(p.Sigmab) - (p.Sigmab[:, None] * (Q.T @ np.linalg.solve(Kt, Q))) * p.Sigmab[None, :]
+    assert np.allclose(mu, mu2, rtol=1e-9) and np.allclose(S, S2, rtol=1e-7, atol=1e-9)
+
+
+def test_transforms_roundtrip():
+    x = np.array([-30.0, -2.0, 0.0, 3.0, 40.0])
+    assert np.allclose(oracle.invmakepositive(oracle.makepositive(x)), x, rtol=1e-9, atol=1e-9)
+    r = np.array([0.101, 1.0, 150.0, 299.999])
+    assert np.allclose(oracle.transformbetween(oracle.invtransformbetween(r, 0.1, 300.0), 0.1, 300.0), r, rtol=1e-12)
+
+
+def test_getprobabilities_and_prior():
+    ll = np.array([[-150.0, -149.0], [-np.inf, -148.5]])
+    p = oracle.getprobabilities(ll)
+    assert p.shape == ll.shape and p.sum() == pytest.approx(1.0) and p[1, 0] == 0.0     # shape preserving, -Inf -> 0
+    assert np.allclose(oracle.getprobabilities(ll + 7.0), p)
+    prior = oracle.uniformpriordelay(L=1e44, z=0.0)
+    assert prior.b == pytest.approx(10 ** 1.559, rel=1e-12)                               # uniformpriordelay.jl:12
+    lp = prior.logpdf(np.array([[1.0, 40.0], [2.0, 3.0]]))
+    q = oracle.getprobabilities(ll, lp)
+    assert q[0, 1] == 0.0 and q.sum() == pytest.approx(1.0)
+
+
+def test_nelder_mead_minimises_quadratic():
+    from oracle.fit import nelder_mead
+    x, fx, it, calls = nelder_mead(lambda v: float(np.sum((v - np.array([1.0, -2.0, 0.5])) ** 2)), np.zeros(3), 1000, 1e-10)
+    assert np.allclose(x, [1.0, -2.0, 0.5], atol=1e-4) and it < 1000
+
+
+@pytest.mark.parametrize("name", ["loglik_2band_matern32", "loglik_3band_OU", "loglik_3band_rbf", "loglik_3band_matern52",
+                                  "loglik_3x64_matern52", "loglik_ragged_OU", "loglik_single_band_rbf"])
+def test_oracle_reproduces_golden_loglik(name):
+    g = load_golden(name)
+    p = oracle.Problem(g["tb"], g["yb"], g["sb"], g["kernel"])
+    for m in range(len(g["rho"])):
+        ll, gr = p.loglik_grad(g["delays"][m], g["alpha"][m], g["rho"][m])
+        assert ll == pytest.approx(g["loglik"][m], rel=1e-12)
+        assert np.allclose(gr, g["grad"][m], rtol=1e-8, atol=1e-9)
+
+
+def test_oracle_reproduces_golden_fit_and_posterior():
+    g = load_golden("fit_cfg1_cfg2")
+    r = oracle.gpcc(g["tb"], g["yb"], g["sb"], kernel="matern32", delays=g["truedelays"], iterations=1000, rhomax=300.0,
+                    theta0=g["theta0"][None], optimizer="lbfgs")
+    assert r[0] == pytest.approx(float(g["loglikel"]), abs=1e-7)
+    # the reference's optimiser (Nelder-Mead, g_tol=1e-6) stops a little short of the L-BFGS optimum
+    assert float(g["loglikel"]) >= float(g["loglikel_nm"]) - 1e-9
+    assert abs(float(g["loglikel"]) - float(g["loglikel_nm"])) < 1e-4
+    assert np.allclose(r[2][1][0], g["postb_mu"], rtol=1e-6)
+    post = oracle.getprobabilities(g["ll_grid"])
+    assert np.allclose(post, g["post_flat"]) and g["cands"][np.argmax(post)] == pytest.approx(2.1)   # true delay 2.0
+    assert np.max(np.abs(oracle.getprobabilities(g["ll_grid_nm"]) - post)) < 1e-4
+
+
+def test_posterior_mode_near_true_delays_3band():
+    g = load_golden("fit_cfg3_subgrid")
+    assert np.allclose(g["delays"][np.argmax(g["post"])], [0.0, 2.0, 4.0])
+    assert g["post"].sum() == pytest.approx(1.0)
