@@ -6,6 +6,8 @@
 
 namespace gpcc {
 
+constexpr int MAX_BANDS = 8;   // == GPCC_MAX_BANDS
+
 // Problem data resident on one device (uploaded once by gpcc_problem_create).
 struct DevProblem {
     int N = 0;            // total points

@@ -1,8 +1,775 @@
-// placeholder (replaced below in this round): tiled large-N path
+// Large-N path: the matrix lives in HBM in a tile layout, factorised / inverted by a blocked symmetric sweep whose
+// flops run on the FP64 tensor pipe (DMMA.8x8x4 = mma.sync.m8n8k4.f64; tcgen05 has no f64 kind).
+//
+// Replaces, for N too large for the register-resident kernel, the same reference code as small_sweep.cu:
+//   K = delayedCovariance(...) + Sobs + B ; logpdf(MvNormal(bbar, K), Y)      (gpccfixdelay_marginaliseb.jl:133-141)
+// plus K^-1 for the analytic gradient (north_star).
+//
+// Data layout (per matrix, lower triangle only):  macro tiles 128x128, tile (I,J), I>=J at index I(I+1)/2+J, each a
+// 16x16 grid of 8x8 micro tiles stored row-major -- exactly the DMMA accumulator fragment (lane t owns elements
+// 2t, 2t+1 of a micro tile), so every global access of the GEMM kernels is a fully coalesced 512-byte warp
+// transaction.  Panels (N x 128 operands) are stored as [k/4][row/8][8 rows x 4 k] chunks = the DMMA A/B fragment,
+// contiguous 16 KB per 16-wide K slice, so they are staged into shared memory with cp.async.bulk (TMA bulk copy
+// engine) completing on an mbarrier, and read back with conflict-free LDS.64.
+//
+// Algorithm, block step k = 0..T-1 (pivot block D = A_kk, 128x128):
+//   pivot   : D = L L' (in shared memory), Linv = L^-1, logdet += 2 sum log L_jj, z = Linv r_k, quad += z'z;
+//             sweep mode also Dinv = Linv' Linv, A_kk <- -Dinv, r_k <- Linv' z.
+//   gather  : column k of the symmetric matrix -> panel layout P (tiles (I,k), I>k and (k,I)' for I<k)
+//   panel   : X = P Linv'   (DMMA)  -> panel layout;  r_I -= X_I z;   sweep mode also Q = P Dinv -> written back as
+//             column k;  forward mode writes X back (the matrix then holds the Cholesky factor).
+//   update  : A_IJ -= X_I X_J'  (DMMA) for all lower tiles with I,J != k (sweep) or I,J > k (forward = Cholesky).
+// Forward mode is exactly a right-looking blocked Cholesky (N^3/3 flop); sweep mode continues the elimination over
+// the already-processed part and leaves -A^-1 (N^3 flop, the same as potrf+potri) with a = A^-1 r in r.
 #include "gpcc_internal.h"
+#include "kernfun.cuh"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
 namespace gpcc {
-cudaError_t large_eval(const DevProblem&, const EvalBatch&, LargeWorkspace&, cudaStream_t, bool, LargeTimings*) {
-    return cudaErrorNotSupported;
+namespace {
+
+constexpr int BT = 128;            // macro tile edge
+constexpr int TILE_ELEMS = BT * BT;
+constexpr int KCH = 16;            // K slice staged per pipeline stage
+constexpr int NCHUNK = BT / KCH;   // 8
+constexpr int STAGES = 3;
+constexpr int CHUNK_ELEMS = KCH * BT;           // 2048 doubles = 16 KB per operand per stage
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+
+__host__ __device__ __forceinline__ size_t tile_index(int I, int J) { return (size_t)I * (I + 1) / 2 + J; }
+// element (r,c) inside a macro tile (tile layout)
+__device__ __forceinline__ int tl_off(int r, int c) { return (((r >> 3) * 16 + (c >> 3)) << 6) + ((r & 7) << 3) + (c & 7); }
+// element (row r, k index c) inside a 128x128 panel block (panel layout)
+__device__ __forceinline__ int pl_off(int r, int c) { return (((c >> 2) * 16 + (r >> 3)) << 5) + ((r & 7) << 2) + (c & 3); }
+
+struct LargeArgs {
+    int N, L, T, Np, kid;
+    int sweep;          // 1: full symmetric sweep (inverse, gradient); 0: forward only (Cholesky, logL)
+    int mode_postb;
+    double* mats;       // [B][ntiles][TILE_ELEMS]
+    double* Pws;        // [B][T][TILE_ELEMS]   gathered column, panel layout
+    double* Xws;        // [B][T][TILE_ELEMS]   X = P Linv', panel layout
+    double* Linv;       // [B][TILE_ELEMS]      Linv[c][k], panel layout
+    double* Dinv;       // [B][TILE_ELEMS]      Dinv[c][k], panel layout
+    double* rvec;       // [B][Np]
+    double* zk;         // [B][BT]
+    double* scal;       // [B][4]  logdet, quad
+    int* info;          // [B]
+    double* tsh;        // [B][Np] shifted times
+    double* av;         // [B][Np] alpha per point (0 on padding)
+    double* part;       // [B][T][T][BT] gradient row-sum partials
+    double* epart;      // [B][ntiles]
+    size_t mat_stride;  // doubles per matrix
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA engine, 1-D), DMMA
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-void large_workspace_release(LargeWorkspace&) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 128x128x128 DMMA main loop shared by the panel and update kernels.
+// acc += sign * A B',  A and B are 128x128 panel-layout blocks in global memory (contiguous 16 KB per K slice).
+// 8 warps; warp w owns rows 32*(w&3).., cols 64*(w>>2)..  -> acc[4][8][2] per lane.
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmSmem {
+    double a[STAGES][CHUNK_ELEMS];
+    double b[STAGES][CHUNK_ELEMS];
+    uint64_t full[STAGES];
+};
+
+__device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* __restrict__ gA, const double* __restrict__ gB,
+                                              double (&acc)[4][8][2], bool negate) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ro0 = (warp & 3) * 4, co0 = (warp >> 2) * 8;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_expect_tx(&sm.full[s], 2 * CHUNK_ELEMS * sizeof(double));
+            bulk_g2s(sm.a[s], gA + (size_t)s * CHUNK_ELEMS, CHUNK_ELEMS * sizeof(double), &sm.full[s]);
+            bulk_g2s(sm.b[s], gB + (size_t)s * CHUNK_ELEMS, CHUNK_ELEMS * sizeof(double), &sm.full[s]);
+        }
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int s = ch % STAGES;
+        mbar_wait(&sm.full[s], (ch / STAGES) & 1);
+        const double* sa = sm.a[s];
+        const double* sb = sm.b[s];
+#pragma unroll
+        for (int k4 = 0; k4 < KCH / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = sa[((k4 * 16 + ro0 + i) << 5) + lane];
+                if (negate) a[i] = -a[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = sb[((k4 * 16 + co0 + j) << 5) + lane];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();   // everyone is done with stage s
+        if (tid == 0 && ch + STAGES < NCHUNK) {
+            mbar_expect_tx(&sm.full[s], 2 * CHUNK_ELEMS * sizeof(double));
+            bulk_g2s(sm.a[s], gA + (size_t)(ch + STAGES) * CHUNK_ELEMS, CHUNK_ELEMS * sizeof(double), &sm.full[s]);
+            bulk_g2s(sm.b[s], gB + (size_t)(ch + STAGES) * CHUNK_ELEMS, CHUNK_ELEMS * sizeof(double), &sm.full[s]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep: shifted times, per-point alpha, right-hand side
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void prep_kernel(DevProblem p, EvalBatch b, int e0, LargeArgs a) {
+    const int m = blockIdx.y, e = e0 + m;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.Np; i += gridDim.x * blockDim.x) {
+        double ts = 0.0, al = 0.0, r = 0.0;
+        if (i < a.N) {
+            const int bi = p.band[i];
+            ts = p.t[i] - b.delays[(size_t)e * a.L + bi];     // delayedCovariance.jl:27
+            al = b.alpha[(size_t)e * a.L + bi];
+            r = a.mode_postb ? p.y[i] : p.resid[i];
+        }
+        a.tsh[(size_t)m * a.Np + i] = ts;
+        a.av[(size_t)m * a.Np + i] = al;
+        a.rvec[(size_t)m * a.Np + i] = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) a.scal[(size_t)m * 4 + threadIdx.x] = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.info[m] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: covariance assembly into the tile layout (HBM-write bound: 4 N (N+1) bytes of unique output per matrix).
+// One CTA per lower macro tile; the 128 row times and 128 column times are staged in shared memory; every warp
+// store is one coalesced 512-byte micro tile (16-byte vector stores).
+// ---------------------------------------------------------------------------------------------------------------
+template <int KID>
+__global__ void __launch_bounds__(256) assemble_kernel(DevProblem p, EvalBatch b, int e0, LargeArgs a) {
+    __shared__ double tr[BT], tc[BT], ar[BT], ac[BT], dr[BT], sr[BT];
+    __shared__ int br[BT], bc[BT];
+    const int m = blockIdx.y, e = e0 + m;
+    // decode lower tile index
+    const int tix = blockIdx.x;
+    int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+    while ((size_t)I * (I + 1) / 2 > (size_t)tix) --I;
+    while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tix) ++I;
+    const int J = tix - I * (I + 1) / 2;
+    const int tid = threadIdx.x;
+    if (tid < BT) {
+        const int i = I * BT + tid;
+        tr[tid] = a.tsh[(size_t)m * a.Np + i];
+        ar[tid] = a.av[(size_t)m * a.Np + i];
+        dr[tid] = i < a.N ? p.s2[i] : 0.0;
+        sr[tid] = (i < a.N && !a.mode_postb) ? p.sigb[i] : 0.0;
+        br[tid] = i < a.N ? p.band[i] : -1 - i;
+    } else {
+        const int c = tid - BT, j = J * BT + c;
+        tc[c] = a.tsh[(size_t)m * a.Np + j];
+        ac[c] = a.av[(size_t)m * a.Np + j];
+        bc[c] = j < a.N ? p.band[j] : -1 - j;
+    }
+    __syncthreads();
+    const KernParams kp = make_kern_params(KID, b.rho[e]);
+    double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int rr = lane >> 2, cc = (lane & 3) * 2;
+    for (int mt = warp; mt < 256; mt += 8) {       // micro tile (mi, mj)
+        const int mi = mt >> 4, mj = mt & 15;
+        const int r = mi * 8 + rr, c = mj * 8 + cc;
+        const int gi = I * BT + r;
+        double v[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int gj = J * BT + c + q;
+            double val = (ar[r] * ac[c + q]) * kern_value<KID>(tr[r] - tc[c + q], kp);   // delayedCovariance.jl:27
+            if (gi == gj) val += dr[r];                                                      // + Sobs (:135)
+            if (br[r] == bc[c + q]) val += sr[r];                                            // + B
+            if (gi >= a.N && gi == gj) val = 1.0;                                            // identity on the padding
+            v[q] = val;
+        }
+        *reinterpret_cast<double2*>(tile + (mt << 6) + 2 * lane) = make_double2(v[0], v[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pivot: Cholesky + triangular inverse of the 128x128 diagonal block in shared memory (one CTA per matrix)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, row-major
+
+__global__ void __launch_bounds__(256) pivot_kernel(LargeArgs a, int k) {
+    extern __shared__ double sh[];
+    double* Lp = sh;                         // packed lower L      (8256 doubles)
+    double* Li = sh + BT * (BT + 1) / 2;     // packed lower Linv
+    double* zz = Li + BT * (BT + 1) / 2;     // [BT]
+    double* rk = zz + BT;                    // [BT]
+    __shared__ int s_bad;
+    const int m = blockIdx.x, tid = threadIdx.x;
+    double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(k, k) * TILE_ELEMS;
+    for (int e = tid; e < BT * BT; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        if (c <= r) Lp[pk(r, c)] = tile[tl_off(r, c)];
+    }
+    if (tid < BT) rk[tid] = a.rvec[(size_t)m * a.Np + k * BT + tid];
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    // right-looking Cholesky, column by column
+    for (int j = 0; j < BT; ++j) {
+        const double d = Lp[pk(j, j)];
+        if (!(d > 0.0)) { if (tid == 0 && s_bad == 0) s_bad = j + 1; }
+        const double s = sqrt(d), inv = 1.0 / s;
+        __syncthreads();
+        if (tid == 0) Lp[pk(j, j)] = s;
+        for (int i = j + 1 + tid; i < BT; i += 256) Lp[pk(i, j)] *= inv;
+        __syncthreads();
+        const int nrem = BT - j - 1;
+        for (int e = tid; e < nrem * nrem; e += 256) {
+            const int ii = e / nrem, cc = e - ii * nrem;
+            if (cc <= ii) {
+                const int i = j + 1 + ii, c = j + 1 + cc;
+                Lp[pk(i, c)] = fma(-Lp[pk(i, j)], Lp[pk(c, j)], Lp[pk(i, c)]);
+            }
+        }
+        __syncthreads();
+    }
+    // Linv: thread j solves L x = e_j (column j of the inverse)
+    if (tid < BT) {
+        const int j = tid;
+        Li[pk(j, j)] = 1.0 / Lp[pk(j, j)];
+        for (int i = j + 1; i < BT; ++i) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four chains: the FMA latency, not the pipe, bounds this loop
+            int q = j;
+            for (; q + 3 < i; q += 4) {
+                s0 = fma(Lp[pk(i, q)], Li[pk(q, j)], s0);
+                s1 = fma(Lp[pk(i, q + 1)], Li[pk(q + 1, j)], s1);
+                s2 = fma(Lp[pk(i, q + 2)], Li[pk(q + 2, j)], s2);
+                s3 = fma(Lp[pk(i, q + 3)], Li[pk(q + 3, j)], s3);
+            }
+            for (; q < i; ++q) s0 = fma(Lp[pk(i, q)], Li[pk(q, j)], s0);
+            Li[pk(i, j)] = -((s0 + s1) + (s2 + s3)) / Lp[pk(i, i)];
+        }
+    }
+    __syncthreads();
+    // z = Linv r_k ; quad += z'z ; logdet += 2 sum log L_jj
+    if (tid < BT) {
+        double s = 0.0;
+        for (int q = 0; q <= tid; ++q) s = fma(Li[pk(tid, q)], rk[q], s);
+        zz[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double q = 0.0, ld = 0.0;
+        for (int i = 0; i < BT; ++i) { q = fma(zz[i], zz[i], q); ld += log(Lp[pk(i, i)]); }
+        a.scal[(size_t)m * 4 + 0] += 2.0 * ld;
+        a.scal[(size_t)m * 4 + 1] += q;
+        if (s_bad && a.info[m] == 0) a.info[m] = k * BT + s_bad;
+    }
+    if (tid < BT) a.zk[(size_t)m * BT + tid] = zz[tid];
+    // Linv in panel layout: element (c, kk) = Linv[c][kk]
+    double* gL = a.Linv + (size_t)m * TILE_ELEMS;
+    for (int e = tid; e < BT * BT; e += 256) {
+        const int c = e >> 7, kk = e & 127;
+        gL[pl_off(c, kk)] = (kk <= c) ? Li[pk(c, kk)] : 0.0;
+    }
+    if (a.sweep) {
+        // r_k <- Linv' z  (= D^-1 r_k)
+        if (tid < BT) {
+            double s = 0.0;
+            for (int q = tid; q < BT; ++q) s = fma(Li[pk(q, tid)], zz[q], s);
+            a.rvec[(size_t)m * a.Np + k * BT + tid] = s;
+        }
+        // Dinv = Linv' Linv ; A_kk <- -Dinv
+        double* gD = a.Dinv + (size_t)m * TILE_ELEMS;
+        for (int e = tid; e < BT * BT; e += 256) {
+            const int r = e >> 7, c = e & 127;
+            const int q0 = r > c ? r : c;
+            double s = 0.0;
+            for (int q = q0; q < BT; ++q) s = fma(Li[pk(q, r)], Li[pk(q, c)], s);
+            gD[pl_off(r, c)] = s;
+            tile[tl_off(r, c)] = -s;
+        }
+    } else {
+        // forward mode: leave the Cholesky factor in the diagonal tile
+        for (int e = tid; e < BT * BT; e += 256) {
+            const int r = e >> 7, c = e & 127;
+            tile[tl_off(r, c)] = (c <= r) ? Lp[pk(r, c)] : 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gather column k of the symmetric matrix into panel layout
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(LargeArgs a, int k, int I0) {
+    const int m = blockIdx.y;
+    int I = I0 + blockIdx.x;
+    if (a.sweep && I >= k) ++I;           // skip the pivot block row
+    const double* mat = a.mats + (size_t)m * a.mat_stride;
+    double* out = a.Pws + ((size_t)m * a.T + I) * TILE_ELEMS;
+    if (I > k) {
+        const double* tile = mat + tile_index(I, k) * TILE_ELEMS;
+        for (int e = threadIdx.x; e < TILE_ELEMS / 2; e += 256) {      // e indexes double2 in panel layout
+            const int o = e * 2;
+            const int c4 = o & 3, r8 = (o >> 2) & 7, ro = (o >> 5) & 15, k4 = o >> 9;
+            const int r = ro * 8 + r8, c = k4 * 4 + c4;
+            *reinterpret_cast<double2*>(out + o) = *reinterpret_cast<const double2*>(tile + tl_off(r, c));
+        }
+    } else {
+        const double* tile = mat + tile_index(k, I) * TILE_ELEMS;      // P = tile'
+        for (int e = threadIdx.x; e < TILE_ELEMS; e += 256) {
+            const int c4 = e & 3, r8 = (e >> 2) & 7, ro = (e >> 5) & 15, k4 = e >> 9;
+            const int r = ro * 8 + r8, c = k4 * 4 + c4;
+            out[e] = tile[tl_off(c, r)];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// panel: X = P Linv' (which==0) -> panel layout (+ r_I -= X z, + forward mode write-back);  Q = P Dinv (which==1) ->
+// column k of the matrix.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I0) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    const int m = blockIdx.y, which = blockIdx.z;
+    int I = I0 + blockIdx.x;
+    if (a.sweep && I >= k) ++I;
+    const double* gA = a.Pws + ((size_t)m * a.T + I) * TILE_ELEMS;
+    const double* gB = (which == 0 ? a.Linv : a.Dinv) + (size_t)m * TILE_ELEMS;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    gemm_mainloop(sm, gA, gB, acc, false);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ro0 = (warp & 3) * 4, co0 = (warp >> 2) * 8;
+    double* mat = a.mats + (size_t)m * a.mat_stride;
+    if (which == 0) {
+        double* xo = a.Xws + ((size_t)m * a.T + I) * TILE_ELEMS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int mi = ro0 + i, mj = co0 + j;
+                const int off = (((2 * mj + ((lane & 3) >> 1)) * 16 + mi) << 5) + ((lane >> 2) << 2) + ((lane & 1) << 1);
+                *reinterpret_cast<double2*>(xo + off) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        // r_I -= X_I z_k  : partial dot over this warp's 64 columns, combined through shared memory
+        double* red = reinterpret_cast<double*>(smraw);      // reuse stage memory (main loop is finished)
+        __syncthreads();
+        const double* z = a.zk + (size_t)m * BT;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = (co0 + j) * 8 + (lane & 3) * 2;
+                s = fma(acc[i][j][0], z[c], s);
+                s = fma(acc[i][j][1], z[c + 1], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if ((lane & 3) == 0) red[(warp >> 2) * BT + (ro0 + i) * 8 + (lane >> 2)] = s;
+        }
+        __syncthreads();
+        if (tid < BT) a.rvec[(size_t)m * a.Np + I * BT + tid] -= red[tid] + red[BT + tid];
+        if (!a.sweep) {   // forward mode: keep L in the matrix (tile (I,k), I>k)
+            double* tile = mat + tile_index(I, k) * TILE_ELEMS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<double2*>(tile + (((ro0 + i) * 16 + co0 + j) << 6) + 2 * lane) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    } else {
+        if (I > k) {
+            double* tile = mat + tile_index(I, k) * TILE_ELEMS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<double2*>(tile + (((ro0 + i) * 16 + co0 + j) << 6) + 2 * lane) = make_double2(acc[i][j][0], acc[i][j][1]);
+        } else {       // stored transposed in tile (k, I)
+            double* tile = mat + tile_index(k, I) * TILE_ELEMS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = (ro0 + i) * 8 + (lane >> 2), c = (co0 + j) * 8 + (lane & 3) * 2;
+                    tile[tl_off(c, r)] = acc[i][j][0];
+                    tile[tl_off(c + 1, r)] = acc[i][j][1];
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// update: A_IJ -= X_I X_J'  for the lower tiles not touching block k (sweep) / beyond block k (forward)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    const int m = blockIdx.y;
+    const int tix = blockIdx.x;
+    int Ir = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+    while ((size_t)Ir * (Ir + 1) / 2 > (size_t)tix) --Ir;
+    while ((size_t)(Ir + 1) * (Ir + 2) / 2 <= (size_t)tix) ++Ir;
+    const int Jr = tix - Ir * (Ir + 1) / 2;
+    int I, J;
+    if (a.sweep) { I = Ir + (Ir >= k); J = Jr + (Jr >= k); }
+    else { I = Ir + k + 1; J = Jr + k + 1; }
+    const double* gA = a.Xws + ((size_t)m * a.T + I) * TILE_ELEMS;
+    const double* gB = a.Xws + ((size_t)m * a.T + J) * TILE_ELEMS;
+    double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ro0 = (warp & 3) * 4, co0 = (warp >> 2) * 8;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {      // acc = C (coalesced 512 B per warp per micro tile); overlaps the pipeline fill
+            const double2 v = *reinterpret_cast<const double2*>(tile + (((ro0 + i) * 16 + co0 + j) << 6) + 2 * lane);
+            acc[i][j][0] = v.x;
+            acc[i][j][1] = v.y;
+        }
+    gemm_mainloop(sm, gA, gB, acc, true);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<double2*>(tile + (((ro0 + i) * 16 + co0 + j) << 6) + 2 * lane) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gradient: W = a a' - A^-1 contracted with K and dK/drho, one CTA per lower tile (one read of the inverse)
+// ---------------------------------------------------------------------------------------------------------------
+template <int KID>
+__global__ void __launch_bounds__(256) gradreduce_kernel(EvalBatch b, int e0, LargeArgs a) {
+    __shared__ double tr[BT], tc[BT], ar[BT], ac[BT], wr[BT], wc[BT];
+    __shared__ double rows[1][BT], cols[8][BT];
+    __shared__ double esum[8];
+    const int m = blockIdx.y, e = e0 + m;
+    const int tix = blockIdx.x;
+    int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+    while ((size_t)I * (I + 1) / 2 > (size_t)tix) --I;
+    while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tix) ++I;
+    const int J = tix - I * (I + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < BT) {
+        const int i = I * BT + tid;
+        tr[tid] = a.tsh[(size_t)m * a.Np + i]; ar[tid] = a.av[(size_t)m * a.Np + i]; wr[tid] = i < a.N ? a.rvec[(size_t)m * a.Np + i] : 0.0;
+    } else {
+        const int c = tid - BT, j = J * BT + c;
+        tc[c] = a.tsh[(size_t)m * a.Np + j]; ac[c] = a.av[(size_t)m * a.Np + j]; wc[c] = j < a.N ? a.rvec[(size_t)m * a.Np + j] : 0.0;
+    }
+    for (int q = tid; q < 8 * BT; q += 256) (&cols[0][0])[q] = 0.0;
+    if (tid < BT) rows[0][tid] = 0.0;
+    __syncthreads();
+    const KernParams kp = make_kern_params(KID, b.rho[e]);
+    const double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
+    const int rr = lane >> 2, cc = (lane & 3) * 2;
+    double es = 0.0;
+    // warp w handles micro-tile rows mi = 2w, 2w+1 (all 16 mj): row sums stay in the warp, column sums go to cols[w][]
+    for (int mi = 2 * warp; mi < 2 * warp + 2; ++mi) {
+        const int r = mi * 8 + rr;
+        double rsum = 0.0;
+        for (int mj = 0; mj < 16; ++mj) {
+            const double2 v = *reinterpret_cast<const double2*>(tile + ((mi * 16 + mj) << 6) + 2 * lane);
+            const double vv[2] = {v.x, v.y};
+            double csum[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = mj * 8 + cc + q;
+                const int gi = I * BT + r, gj = J * BT + c;
+                const double W = fma(wr[r], wc[c], vv[q]);              // a_i a_j - (A^-1)_ij   (matrix holds -A^-1)
+                double kv, dkv;
+                kern_value_drho<KID>(tr[r] - tc[c], kp, kv, dkv);
+                const double aa = ar[r] * ac[c];
+                double ct = W * (aa * kv), et = W * (aa * dkv);
+                if (I == J) {
+                    if (gi == gj) { rsum += ct; ct = 0.0; et = 0.0; }
+                    else if (gj > gi) { ct = 0.0; et = 0.0; }
+                }
+                rsum += ct;
+                csum[q] = ct;
+                es += et;
+            }
+            // column sums over the 8 rows of this micro tile: lanes with equal (lane&3) hold the same columns
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double s = csum[q];
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (rr == 0) cols[warp][mj * 8 + cc + q] += s;
+            }
+        }
+        rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
+        rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+        if ((lane & 3) == 0) rows[0][r] = rsum;
+    }
+    for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+    if (lane == 0) esum[warp] = es;
+    __syncthreads();
+    double* part = a.part + (size_t)m * a.T * a.T * BT;
+    if (tid < BT) {
+        double cs = 0.0;
+        for (int w = 0; w < 8; ++w) cs += cols[w][tid];
+        if (I == J) {
+            part[((size_t)I * a.T + J) * BT + tid] = rows[0][tid] + cs;
+        } else {
+            part[((size_t)I * a.T + J) * BT + tid] = rows[0][tid];
+            part[((size_t)J * a.T + I) * BT + tid] = cs;
+        }
+    }
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += esum[w];
+        a.epart[(size_t)m * (a.T * (a.T + 1) / 2) + tix] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(DevProblem p, EvalBatch b, int e0, LargeArgs a) {
+    __shared__ double red[8];
+    __shared__ double srow_band[MAX_BANDS];
+    const int m = blockIdx.x, e = e0 + m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int info = a.info[m];
+    const double ll = -0.5 * ((double)a.N * LOG2PI + a.scal[(size_t)m * 4 + 0] + a.scal[(size_t)m * 4 + 1]);
+    if (tid == 0) {
+        b.ll[e] = info ? -INFINITY : ll;
+        if (b.info) b.info[e] = info;
+    }
+    if (!b.want_grad) return;
+    if (info) { if (tid <= a.L) b.grad[(size_t)e * (a.L + 1) + tid] = 0.0; return; }
+    const double* part = a.part + (size_t)m * a.T * a.T * BT;
+    for (int pb = 0; pb < a.L; ++pb) {
+        double s = 0.0;
+        for (int i = p.band_start[pb] + tid; i < p.band_start[pb + 1]; i += 256) {
+            const int I = i >> 7, r = i & 127;
+            double si = 0.0;
+            for (int src = 0; src < a.T; ++src) si += part[((size_t)I * a.T + src) * BT + r];
+            s += si;
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double v = 0.0;
+            for (int w = 0; w < 8; ++w) v += red[w];
+            srow_band[pb] = v;
+        }
+    }
+    double es = 0.0;
+    const int nt = a.T * (a.T + 1) / 2;
+    for (int q = tid; q < nt; q += 256) es += a.epart[(size_t)m * nt + q];
+    for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = es;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w];
+        for (int pb = 0; pb < a.L; ++pb) b.grad[(size_t)e * (a.L + 1) + pb] = srow_band[pb] / b.alpha[(size_t)e * a.L + pb];
+        b.grad[(size_t)e * (a.L + 1) + a.L] = v;
+    }
+}
+
+// dense column-major K^-1 (both triangles) and a, for postb / pred
+__global__ void dump_kernel(EvalBatch b, int e0, LargeArgs a) {
+    const int m = blockIdx.y, e = e0 + m;
+    const double* mat = a.mats + (size_t)m * a.mat_stride;
+    double* out = b.dump_kinv + (size_t)e * a.N * a.N;
+    const size_t total = (size_t)a.N * a.N;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(q % a.N), j = (int)(q / a.N);
+        const int r = i >= j ? i : j, c = i >= j ? j : i;
+        out[q] = -mat[tile_index(r >> 7, c >> 7) * TILE_ELEMS + tl_off(r & 127, c & 127)];
+    }
+    if (b.dump_a && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < a.N; i += blockDim.x) b.dump_a[(size_t)e * a.N + i] = a.rvec[(size_t)m * a.Np + i];
+}
+
+struct LargeImpl {
+    int N = 0, T = 0, Np = 0, B = 0;
+    size_t mat_stride = 0;
+    double *mats = nullptr, *Pws = nullptr, *Xws = nullptr, *Linv = nullptr, *Dinv = nullptr, *rvec = nullptr, *zk = nullptr,
+           *scal = nullptr, *tsh = nullptr, *av = nullptr, *part = nullptr, *epart = nullptr;
+    int* info = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool attr_set = false;
+    void release() {
+        for (double* p : {mats, Pws, Xws, Linv, Dinv, rvec, zk, scal, tsh, av, part, epart}) if (p) cudaFree(p);
+        if (info) cudaFree(info);
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        mats = Pws = Xws = Linv = Dinv = rvec = zk = scal = tsh = av = part = epart = nullptr;
+        info = nullptr;
+        B = 0;
+    }
+};
+
+cudaError_t ensure(LargeImpl& w, int N, int want_B) {
+    const int T = (N + BT - 1) / BT;
+    if (w.N == N && w.B >= want_B) return cudaSuccess;
+    w.release();
+    w.N = N; w.T = T; w.Np = T * BT;
+    const size_t ntiles = (size_t)T * (T + 1) / 2;
+    w.mat_stride = ntiles * TILE_ELEMS;
+    size_t free_b = 0, total_b = 0;
+    cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+    if (e != cudaSuccess) return e;
+    const size_t per = (w.mat_stride + 2 * (size_t)T * TILE_ELEMS + 2 * TILE_ELEMS + (size_t)T * T * BT + ntiles + 4 * (size_t)w.Np) * sizeof(double);
+    int B = want_B;
+    while (B > 1 && (size_t)B * per > free_b / 2) B /= 2;
+    if ((size_t)B * per > free_b) return cudaErrorMemoryAllocation;
+    w.B = B;
+#define ALLOC(ptr, n) if ((e = cudaMalloc(&ptr, (size_t)(n) * sizeof(*ptr))) != cudaSuccess) return e;
+    ALLOC(w.mats, (size_t)B * w.mat_stride)
+    ALLOC(w.Pws, (size_t)B * T * TILE_ELEMS)
+    ALLOC(w.Xws, (size_t)B * T * TILE_ELEMS)
+    ALLOC(w.Linv, (size_t)B * TILE_ELEMS)
+    ALLOC(w.Dinv, (size_t)B * TILE_ELEMS)
+    ALLOC(w.rvec, (size_t)B * w.Np)
+    ALLOC(w.zk, (size_t)B * BT)
+    ALLOC(w.scal, (size_t)B * 4)
+    ALLOC(w.tsh, (size_t)B * w.Np)
+    ALLOC(w.av, (size_t)B * w.Np)
+    ALLOC(w.part, (size_t)B * T * T * BT)
+    ALLOC(w.epart, (size_t)B * ntiles)
+    ALLOC(w.info, (size_t)B)
+#undef ALLOC
+    for (auto& ev : w.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+template <int KID>
+cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, LargeImpl& w, cudaStream_t st, bool profile,
+                     LargeTimings* tm) {
+    LargeArgs a;
+    a.N = p.N; a.L = p.L; a.T = w.T; a.Np = w.Np; a.kid = KID;
+    a.sweep = (b.want_grad || b.dump_kinv) ? 1 : 0;
+    a.mode_postb = b.mode_postb;
+    a.mats = w.mats; a.Pws = w.Pws; a.Xws = w.Xws; a.Linv = w.Linv; a.Dinv = w.Dinv; a.rvec = w.rvec; a.zk = w.zk;
+    a.scal = w.scal; a.info = w.info; a.tsh = w.tsh; a.av = w.av; a.part = w.part; a.epart = w.epart; a.mat_stride = w.mat_stride;
+    const int T = w.T;
+    const int ntiles = T * (T + 1) / 2;
+    const size_t gemm_smem = sizeof(GemmSmem) + 128;
+    const size_t pivot_smem = (size_t)(BT * (BT + 1) + 2 * BT) * sizeof(double);
+    if (!w.attr_set) {
+        cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+        cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+        cudaFuncSetAttribute(pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pivot_smem);
+        w.attr_set = true;
+    }
+    long long launches = 0;
+    if (profile) cudaEventRecord(w.ev[0], st);
+    prep_kernel<<<dim3((w.Np + 255) / 256, nb), 256, 0, st>>>(p, b, e0, a);
+    assemble_kernel<KID><<<dim3(ntiles, nb), 256, 0, st>>>(p, b, e0, a);
+    launches += 2;
+    if (profile) cudaEventRecord(w.ev[1], st);
+    for (int k = 0; k < T; ++k) {
+        pivot_kernel<<<nb, 256, pivot_smem, st>>>(a, k);
+        ++launches;
+        const int I0 = a.sweep ? 0 : k + 1;
+        const int nI = a.sweep ? T - 1 : T - 1 - k;
+        if (nI > 0) {
+            gather_kernel<<<dim3(nI, nb), 256, 0, st>>>(a, k, I0);
+            panel_kernel<<<dim3(nI, nb, a.sweep ? 2 : 1), 256, gemm_smem, st>>>(a, k, I0);
+            update_kernel<<<dim3(nI * (nI + 1) / 2, nb), 256, gemm_smem, st>>>(a, k);
+            launches += 3;
+        }
+    }
+    if (profile) cudaEventRecord(w.ev[2], st);
+    if (b.want_grad) {
+        gradreduce_kernel<KID><<<dim3(ntiles, nb), 256, 0, st>>>(b, e0, a);
+        ++launches;
+    }
+    finalize_kernel<<<nb, 256, 0, st>>>(p, b, e0, a);
+    ++launches;
+    if (b.dump_kinv) {
+        dump_kernel<<<dim3(592, nb), 256, 0, st>>>(b, e0, a);
+        ++launches;
+    }
+    if (profile) cudaEventRecord(w.ev[3], st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (profile) {
+        e = cudaEventSynchronize(w.ev[3]);
+        if (e != cudaSuccess) return e;
+        float t01 = 0, t12 = 0, t23 = 0;
+        cudaEventElapsedTime(&t01, w.ev[0], w.ev[1]);
+        cudaEventElapsedTime(&t12, w.ev[1], w.ev[2]);
+        cudaEventElapsedTime(&t23, w.ev[2], w.ev[3]);
+        tm->ms_assembly += t01; tm->ms_factor += t12; tm->ms_gradreduce += t23;
+    }
+    tm->launches += launches;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& ws, cudaStream_t stream, bool profile,
+                       LargeTimings* tm) {
+    if (!ws.impl) ws.impl = new LargeImpl();
+    LargeImpl& w = *static_cast<LargeImpl*>(ws.impl);
+    const int want_B = std::min(b.M, p.N >= 4096 ? 8 : (p.N >= 1024 ? 32 : 128));
+    cudaError_t e = ensure(w, p.N, std::max(want_B, 1));
+    if (e != cudaSuccess) return e;
+    for (int e0 = 0; e0 < b.M; e0 += w.B) {
+        const int nb = std::min(w.B, b.M - e0);
+        switch (p.kernel_id) {
+            case K_OU:  e = run_wave<K_OU>(p, b, e0, nb, w, stream, profile, tm); break;
+            case K_RBF: e = run_wave<K_RBF>(p, b, e0, nb, w, stream, profile, tm); break;
+            case K_M32: e = run_wave<K_M32>(p, b, e0, nb, w, stream, profile, tm); break;
+            default:    e = run_wave<K_M52>(p, b, e0, nb, w, stream, profile, tm); break;
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+void large_workspace_release(LargeWorkspace& ws) {
+    if (!ws.impl) return;
+    LargeImpl* w = static_cast<LargeImpl*>(ws.impl);
+    w->release();
+    delete w;
+    ws.impl = nullptr;
+}
+
 }  // namespace gpcc
