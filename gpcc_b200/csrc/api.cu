@@ -52,22 +52,25 @@ int check_options(const gpcc_fit_options* o) {
 // Evaluate `M` (delay, alpha, rho) triples that already sit in the pinned host mirrors of `s`.
 // Results land in s.ll.h / s.grad.h / s.info.h.
 }  // namespace
-int gpcc::evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv, double* dump_a,
-                             int mode_postb) {
+int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, double* dump_kinv, double* dump_a,
+                      int mode_postb) {
     DeviceState& s = p->ctx->ds[di];
+    EvalSlot& q = s.slot[slot];
     const int L = p->L;
     CUDA_TRY(cudaSetDevice(s.dev));
-    CUDA_TRY(cudaMemcpyAsync(s.delays.d, s.delays.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(s.alpha.d, s.alpha.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(s.rho.d, s.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(q.delays.d, q.delays.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(q.alpha.d, q.alpha.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(q.rho.d, q.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     EvalBatch b;
-    b.M = M; b.delays = s.delays.d; b.alpha = s.alpha.d; b.rho = s.rho.d; b.want_grad = want_grad;
-    b.ll = s.ll.d; b.grad = s.grad.d; b.info = s.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a; b.mode_postb = mode_postb;
+    b.M = M; b.delays = q.delays.d; b.alpha = q.alpha.d; b.rho = q.rho.d; b.want_grad = want_grad;
+    b.ll = q.ll.d; b.grad = q.grad.d; b.info = q.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a; b.mode_postb = mode_postb;
     const bool prof = p->ctx->profiling;
+    q.M = M; q.want_grad = want_grad; q.timed = false;
     if (p->small_path) {
-        if (prof) CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
+        if (prof) CUDA_TRY(cudaEventRecord(q.ev0, s.stream));
         CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, s.stream));
-        if (prof) CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
+        if (prof) CUDA_TRY(cudaEventRecord(q.ev1, s.stream));
+        q.timed = prof;
         s.launches += 1;
     } else {
         LargeTimings lt;
@@ -76,31 +79,47 @@ int gpcc::evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, doub
         s.ms_assembly += lt.ms_assembly; s.ms_factor += lt.ms_factor; s.ms_gradreduce += lt.ms_gradreduce;
         s.ms_eval += lt.ms_assembly + lt.ms_factor + lt.ms_gradreduce;
     }
-    CUDA_TRY(cudaMemcpyAsync(s.ll.h, s.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(q.ll.h, q.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     if (want_grad)
-        CUDA_TRY(cudaMemcpyAsync(s.grad.h, s.grad.d, (size_t)M * (L + 1) * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(s.info.h, s.info.d, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaStreamSynchronize(s.stream));
-    if (prof && p->small_path) {
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
-        s.ms_eval += ms;
-    }
-    s.evals += M;
-    if (want_grad) s.evals_grad += M;
+        CUDA_TRY(cudaMemcpyAsync(q.grad.h, q.grad.d, (size_t)M * (L + 1) * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(q.info.h, q.info.d, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaEventRecord(q.done, s.stream));
     return 0;
 }
 
-int gpcc::reserve_eval(gpcc_problem* p, int di, size_t M) {
+int gpcc::finish_eval(gpcc_problem* p, int di, int slot) {
     DeviceState& s = p->ctx->ds[di];
+    EvalSlot& q = s.slot[slot];
+    CUDA_TRY(cudaSetDevice(s.dev));
+    CUDA_TRY(cudaEventSynchronize(q.done));
+    if (q.timed) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, q.ev0, q.ev1));
+        s.ms_eval += ms;
+    }
+    s.evals += q.M;
+    if (q.want_grad) s.evals_grad += q.M;
+    return 0;
+}
+
+int gpcc::evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv, double* dump_a,
+                             int mode_postb) {
+    int rc = launch_eval(p, di, 0, M, want_grad, dump_kinv, dump_a, mode_postb);
+    if (rc) return rc;
+    return finish_eval(p, di, 0);
+}
+
+int gpcc::reserve_eval(gpcc_problem* p, int di, size_t M, int slot) {
+    DeviceState& s = p->ctx->ds[di];
+    EvalSlot& q = s.slot[slot];
     const int L = p->L;
     CUDA_TRY(cudaSetDevice(s.dev));
-    CUDA_TRY(s.delays.reserve(M * L));
-    CUDA_TRY(s.alpha.reserve(M * L));
-    CUDA_TRY(s.rho.reserve(M));
-    CUDA_TRY(s.ll.reserve(M));
-    CUDA_TRY(s.grad.reserve(M * (L + 1)));
-    CUDA_TRY(s.info.reserve(M));
+    CUDA_TRY(q.delays.reserve(M * L));
+    CUDA_TRY(q.alpha.reserve(M * L));
+    CUDA_TRY(q.rho.reserve(M));
+    CUDA_TRY(q.ll.reserve(M));
+    CUDA_TRY(q.grad.reserve(M * (L + 1)));
+    CUDA_TRY(q.info.reserve(M));
     return 0;
 }
 
@@ -147,6 +166,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
     const int m = (int)idx.size();
     if (m == 0) return 0;
     DeviceState& s = p->ctx->ds[di];
+    EvalSlot& q0 = s.slot[0];
     LbfgsOptions lo;
     lo.max_iter = o.max_iter; lo.gtol = o.gtol; lo.ftol = o.ftol; lo.history = o.history;
 
@@ -164,8 +184,8 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
             for (int j = 0; j < P; ++j) {
                 const size_t e = (c - c0) * P + j;
                 const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + j) * n : theta0 + (size_t)j * n;
-                std::memcpy(s.delays.h + e * L, delays + (size_t)gi * L, L * sizeof(double));
-                unpack_theta(th, L, o, s.alpha.h + e * L, s.rho.h + e, nullptr);
+                std::memcpy(q0.delays.h + e * L, delays + (size_t)gi * L, L * sizeof(double));
+                unpack_theta(th, L, o, q0.alpha.h + e * L, q0.rho.h + e, nullptr);
             }
         }
         rc = evaluate_on_device(p, di, (int)((c1 - c0) * P), 1);
@@ -176,8 +196,8 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
             double bestf = std::numeric_limits<double>::infinity();
             for (int j = 0; j < P; ++j) {          // argmin of -logL, first minimum wins (Julia argmin, :209)
                 const size_t e = (c - c0) * P + j;
-                const double f = -s.ll.h[e];
-                if (s.info.h[e] == 0 && std::isfinite(f) && f < bestf) { bestf = f; best = j; }
+                const double f = -q0.ll.h[e];
+                if (q0.info.h[e] == 0 && std::isfinite(f) && f < bestf) { bestf = f; best = j; }
             }
             LbfgsState& S = st[c];
             S.n = n;
@@ -187,37 +207,73 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
             const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + best) * n : theta0 + (size_t)best * n;
             double a_[LBFGS_MAXN], r_, g_[LBFGS_MAXN];
             unpack_theta(th, L, o, a_, &r_, jac.data());
-            for (int k = 0; k < n; ++k) g_[k] = -s.grad.h[e * n + k] * jac[k];
+            for (int k = 0; k < n; ++k) g_[k] = -q0.grad.h[e * n + k] * jac[k];
             S.start(n, th, bestf, g_, lo);
         }
     }
-    // ---- stage 2: batched L-BFGS ----------------------------------------------------------------------
-    std::vector<int> active;
-    active.reserve(m);
-    for (int c = 0; c < m; ++c) if (st[c].status == LbfgsState::RUNNING) active.push_back(c);
-    rc = reserve_eval(p, di, active.size());
-    if (rc) return rc;
-    while (!active.empty()) {
-        const int na = (int)active.size();
+    // ---- stage 2: batched L-BFGS, software-pipelined over two halves of the candidates -------------------------
+    // While the kernel of one half runs, the host feeds the results of the other half to its L-BFGS state machines
+    // and packs that half's next trial points (the fused small-N path only; one slot for the tiled path, whose
+    // workspace is shared and whose host share is negligible).
+    constexpr size_t MERGE_BELOW = 1024;   // fewer active candidates than this: one batch per round (latency bound)
+    int G = (p->small_path && (size_t)m >= MERGE_BELOW) ? 2 : 1;
+    std::vector<int> active[2];
+    for (int c = 0; c < m; ++c)
+        if (st[c].status == LbfgsState::RUNNING) active[G == 2 ? (c & 1) : 0].push_back(c);
+    bool launched[2] = {false, false};
+    auto pack_and_launch = [&](int g) -> int {
+        EvalSlot& q = s.slot[g];
+        const int na = (int)active[g].size();
         for (int a = 0; a < na; ++a) {
-            const int c = active[a];
-            std::memcpy(s.delays.h + (size_t)a * L, delays + (size_t)idx[c] * L, L * sizeof(double));
-            unpack_theta(st[c].xt, L, o, s.alpha.h + (size_t)a * L, s.rho.h + a, nullptr);
+            const int c = active[g][a];
+            std::memcpy(q.delays.h + (size_t)a * L, delays + (size_t)idx[c] * L, L * sizeof(double));
+            unpack_theta(st[c].xt, L, o, q.alpha.h + (size_t)a * L, q.rho.h + a, nullptr);
         }
-        rc = evaluate_on_device(p, di, na, 1);
-        if (rc) return rc;
+        launched[g] = true;
+        return launch_eval(p, di, g, na, 1);
+    };
+    auto finish_and_feed = [&](int g) -> int {
+        int r = finish_eval(p, di, g);
+        if (r) return r;
+        launched[g] = false;
+        EvalSlot& q = s.slot[g];
+        const int na = (int)active[g].size();
         size_t w = 0;
         for (int a = 0; a < na; ++a) {
-            const int c = active[a];
+            const int c = active[g][a];
             LbfgsState& S = st[c];
             double a_[LBFGS_MAXN], r_, g_[LBFGS_MAXN];
             unpack_theta(S.xt, L, o, a_, &r_, jac.data());
-            const bool ok = s.info.h[a] == 0 && std::isfinite(s.ll.h[a]);
-            for (int k = 0; k < n; ++k) g_[k] = ok ? -s.grad.h[(size_t)a * n + k] * jac[k] : 0.0;
-            S.feed(ok, -s.ll.h[a], g_, lo);
-            if (S.status == LbfgsState::RUNNING) active[w++] = c;
+            const bool ok = q.info.h[a] == 0 && std::isfinite(q.ll.h[a]);
+            for (int k = 0; k < n; ++k) g_[k] = ok ? -q.grad.h[(size_t)a * n + k] * jac[k] : 0.0;
+            S.feed(ok, -q.ll.h[a], g_, lo);
+            if (S.status == LbfgsState::RUNNING) active[g][w++] = c;
         }
-        active.resize(w);
+        active[g].resize(w);
+        return 0;
+    };
+    rc = reserve_eval(p, di, active[0].size() + active[1].size(), 0);
+    if (rc) return rc;
+    rc = reserve_eval(p, di, active[1].size(), 1);
+    if (rc) return rc;
+    for (int g = 0; g < G; ++g)
+        if (!active[g].empty()) { rc = pack_and_launch(g); if (rc) return rc; }
+    while (launched[0] || launched[1]) {
+        for (int g = 0; g < G; ++g) {
+            if (!launched[g]) continue;
+            rc = finish_and_feed(g);
+            if (rc) return rc;
+            if (G == 2 && active[0].size() + active[1].size() < MERGE_BELOW) {
+                const int h = 1 - g;                      // drain the other half, then continue with one batch per round
+                if (launched[h]) { rc = finish_and_feed(h); if (rc) return rc; }
+                active[0].insert(active[0].end(), active[1].begin(), active[1].end());
+                active[1].clear();
+                G = 1;
+                if (!active[0].empty()) { rc = pack_and_launch(0); if (rc) return rc; }
+                break;
+            }
+            if (!active[g].empty()) { rc = pack_and_launch(g); if (rc) return rc; }
+        }
     }
     // ---- outputs ------------------------------------------------------------------------------------------
     for (int c = 0; c < m; ++c) {
@@ -311,8 +367,11 @@ int gpcc_ctx_create(int ndev, const int* dev_ids, gpcc_ctx** out) {
         if (prop.major < 10) { delete ctx; return fail(-4, "libgpcc_b200 is built for sm_100a (Blackwell B200) only"); }
         CUDA_TRY(cudaSetDevice(s.dev));
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreate(&s.ev0));
-        CUDA_TRY(cudaEventCreate(&s.ev1));
+        for (auto& q : s.slot) {
+            CUDA_TRY(cudaEventCreate(&q.ev0));
+            CUDA_TRY(cudaEventCreate(&q.ev1));
+            CUDA_TRY(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+        }
     }
     *out = ctx;
     return 0;
@@ -323,10 +382,13 @@ int gpcc_ctx_destroy(gpcc_ctx* ctx) {
     if (ctx->nccl) nccl_bridge_destroy(ctx->nccl);
     for (auto& s : ctx->ds) {
         cudaSetDevice(s.dev);
-        s.delays.release(); s.alpha.release(); s.rho.release(); s.ll.release(); s.grad.release(); s.info.release();
+        for (auto& q : s.slot) {
+            q.delays.release(); q.alpha.release(); q.rho.release(); q.ll.release(); q.grad.release(); q.info.release();
+            if (q.ev0) cudaEventDestroy(q.ev0);
+            if (q.ev1) cudaEventDestroy(q.ev1);
+            if (q.done) cudaEventDestroy(q.done);
+        }
         large_workspace_release(s.large);
-        if (s.ev0) cudaEventDestroy(s.ev0);
-        if (s.ev1) cudaEventDestroy(s.ev1);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete ctx;
@@ -457,7 +519,7 @@ static int loglik_batch_impl(gpcc_problem* p, int M, const double* delays, const
     const int nd = (int)ctx->ds.size();
     const size_t chunk = 1 << 18;
     int rc = for_each_device(ctx, [&](int di) -> int {
-        DeviceState& s = ctx->ds[di];
+        EvalSlot& s = ctx->ds[di].slot[0];
         std::vector<int> mine;
         for (int m = di; m < M; m += nd) mine.push_back(m);
         std::vector<double> jac(n);

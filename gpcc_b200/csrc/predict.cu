@@ -283,7 +283,7 @@ int inverse_on_device(gpcc_problem* p, const double* delays, const double* alpha
     const int L = p->L;
     int rc = reserve_eval(p, 0, 1);
     if (rc) return rc;
-    DeviceState& s = p->ctx->ds[0];
+    EvalSlot& s = p->ctx->ds[0].slot[0];
     std::memcpy(s.delays.h, delays, L * sizeof(double));
     std::memcpy(s.alpha.h, alpha, L * sizeof(double));
     s.rho.h[0] = rho;

@@ -44,12 +44,21 @@ struct DevBuf {   // growable device buffer + pinned host mirror
     }
 };
 
+// Staging of one in-flight evaluation batch.  Two slots per device let the host-side L-BFGS bookkeeping of one
+// half of the candidates overlap with the kernel of the other half (all work is issued on ONE stream, so kernels
+// never overlap each other and the per-kernel CUDA-event timings stay exact).
+struct EvalSlot {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+    DevBuf<double> delays, alpha, rho, ll, grad;
+    DevBuf<int> info;
+    int M = 0, want_grad = 0;
+    bool timed = false;
+};
+
 struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf<double> delays, alpha, rho, ll, grad;
-    DevBuf<int> info;
+    EvalSlot slot[2];
     LargeWorkspace large;     // tiled large-N path (large_path.cu)
     // per-call statistics (profiling)
     double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
@@ -84,5 +93,9 @@ namespace gpcc {
 // results land in ds[di].ll.h / grad.h / info.h.  Optionally dumps K~^-1 (dense) and a = K~^-1 r.
 int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv = nullptr,
                        double* dump_a = nullptr, int mode_postb = 0);
-int reserve_eval(gpcc_problem* p, int di, size_t M);
+int reserve_eval(gpcc_problem* p, int di, size_t M, int slot = 0);
+// asynchronous pair: launch_eval enqueues H2D + kernel + D2H of slot `slot`; finish_eval waits for it.
+int launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, double* dump_kinv = nullptr, double* dump_a = nullptr,
+                int mode_postb = 0);
+int finish_eval(gpcc_problem* p, int di, int slot);
 }  // namespace gpcc
