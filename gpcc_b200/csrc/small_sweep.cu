@@ -33,13 +33,17 @@ namespace {
 constexpr int TS = SMALL_TILE;  // 8
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
-__device__ __forceinline__ int cidx(int i, int T) {  // chunked layout: [pair-of-rows part][tile][2]
-    return ((i & 7) >> 1) * (2 * T) + ((i >> 3) << 1) + (i & 1);
+// Chunked layout of the per-point vectors in shared memory: [pair-of-rows part (4)][tile (<=32)][2], with a
+// compile-time part stride so that every address in the sweep loop is "per-thread base + immediate".
+constexpr int CS = 64;          // doubles per part (>= 2*SMALL_MAX_T)
+constexpr int VLEN = 4 * CS;    // doubles per vector
+__device__ __forceinline__ int cidx(int i, int /*T*/) {
+    return ((i & 7) >> 1) * CS + ((i >> 3) << 1) + (i & 1);
 }
 __device__ __forceinline__ void load8(const double* buf, int tile, int T, double (&out)[8]) {
 #pragma unroll
     for (int part = 0; part < 4; ++part) {
-        const double2 v = *reinterpret_cast<const double2*>(buf + part * 2 * T + 2 * tile);
+        const double2 v = *reinterpret_cast<const double2*>(buf + part * CS + 2 * tile);
         out[2 * part] = v.x;
         out[2 * part + 1] = v.y;
     }
@@ -47,68 +51,73 @@ __device__ __forceinline__ void load8(const double* buf, int tile, int T, double
 __device__ __forceinline__ void store8(double* buf, int tile, int T, const double (&in)[8]) {
 #pragma unroll
     for (int part = 0; part < 4; ++part)
-        *reinterpret_cast<double2*>(buf + part * 2 * T + 2 * tile) = make_double2(in[2 * part], in[2 * part + 1]);
+        *reinterpret_cast<double2*>(buf + part * CS + 2 * tile) = make_double2(in[2 * part], in[2 * part + 1]);
 }
 
 // Publish column `kn` (tile tkn, in-tile index KKN) of the symmetric matrix for the next sweep step.
+// Scalar STS.64 straight from the tile registers (no staging moves); only warps that contain an owner enter.
 template <int KKN>
 __device__ __forceinline__ void publish(const double (&A)[8][8], int ti, int tj, int tkn, int kn, int T,
-                                        double* nb, double* pslot, double* piv) {
-    if (tj == tkn) {
-        double vals[8];
-        if (ti == tkn) {  // diagonal tile: below the diagonal from the column, above it from the row
+                                        double* nb, double* pslot, double* piv, bool active) {
+    const bool pc = active && (tj == tkn), prw = active && (ti == tkn);
+    if (!__any_sync(0xffffffffu, pc || prw)) return;
+    if (pc) {
+        double* dst = nb + 2 * ti;
+        if (prw) {  // diagonal tile: below the diagonal from the column, above it from the row
 #pragma unroll
-            for (int r = 0; r < 8; ++r) vals[r] = (r >= KKN) ? A[r][KKN] : A[KKN][r];
+            for (int r = 0; r < 8; ++r) dst[(r >> 1) * CS + (r & 1)] = (r >= KKN) ? A[r][KKN] : A[KKN][r];
             const double d = A[KKN][KKN];
             piv[kn] = d;
             *pslot = 1.0 / d;
         } else {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) vals[r] = A[r][KKN];
+            for (int r = 0; r < 8; ++r) dst[(r >> 1) * CS + (r & 1)] = A[r][KKN];
         }
-        store8(nb, ti, T, vals);
-    } else if (ti == tkn) {
-        double vals[8];
+    } else if (prw) {
+        double* dst = nb + 2 * tj;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) vals[c] = A[KKN][c];
-        store8(nb, tj, T, vals);
+        for (int c = 0; c < 8; ++c) dst[(c >> 1) * CS + (c & 1)] = A[KKN][c];
     }
 }
 
 template <int KK>
 __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, int tk, int k, int N, int T, int Np,
                                            double* cbuf, double* pbuf, double* piv, bool active) {
-    const double* cb = cbuf + (k & 1) * Np;
-    double cr[8], v[8];
+    const double* cb = cbuf + (k & 1) * VLEN;
+    double v[8];
     load8(cb, tj, T, v);
     const double pr = pbuf[k & 1];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] *= pr;
+    // Column k of its owner tiles must become c * (1/d).  Those registers hold exactly the broadcast values c, so
+    // running the generic update with the multiplier (1 - 1/d) in that column writes c - c (1 - 1/d) = c/d without
+    // any extra instruction (relative error eps*d in entries of the inverse only; pivots, log-det and the
+    // quadratic form never read the swept region).
+    const bool own_col = (tj == tk), own_row = (ti == tk);
+    const double vkk = v[KK];
+    if (own_col) v[KK] = 1.0 - pr;
 #pragma unroll
     for (int part = 0; part < 4; ++part) {   // rows two at a time: keeps only a pair of broadcast values live
-        const double2 x = *reinterpret_cast<const double2*>(cb + part * 2 * T + 2 * ti);
-        cr[2 * part] = x.x;
-        cr[2 * part + 1] = x.y;
+        const double2 x = *reinterpret_cast<const double2*>(cb + part * CS + 2 * ti);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             A[2 * part][c] = fma(-x.x, v[c], A[2 * part][c]);
             A[2 * part + 1][c] = fma(-x.y, v[c], A[2 * part + 1][c]);
         }
     }
-    if (tj == tk) {
+    v[KK] = vkk;
+    if (__any_sync(0xffffffffu, own_row)) {
+        if (own_row) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) A[r][KK] = cr[r] * pr;
-    }
-    if (ti == tk) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) A[KK][c] = v[c];
-        if (tj == tk) A[KK][KK] = -pr;
+            for (int c = 0; c < 8; ++c) A[KK][c] = v[c];
+            if (own_col) A[KK][KK] = -pr;
+        }
     }
     const int kn = k + 1;
-    if (kn < N && active) {
-        double* nb = cbuf + (kn & 1) * Np;
-        if (KK < 7) publish<(KK + 1) & 7>(A, ti, tj, tk, kn, T, nb, pbuf + (kn & 1), piv);
-        else        publish<0>(A, ti, tj, tk + 1, kn, T, nb, pbuf + (kn & 1), piv);
+    if (kn < N) {
+        double* nb = cbuf + (kn & 1) * VLEN;
+        if (KK < 7) publish<(KK + 1) & 7>(A, ti, tj, tk, kn, T, nb, pbuf + (kn & 1), piv, active);
+        else        publish<0>(A, ti, tj, tk + 1, kn, T, nb, pbuf + (kn & 1), piv, active);
     }
     __syncthreads();
 }
@@ -148,13 +157,13 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
     const int tj = q - ti * (ti + 1) / 2;
 
     double* tsh = smem;             // shifted times t_i - tau_band(i)         (chunk layout)
-    double* av = tsh + Np;          // alpha_band(i), 0 for padding            (chunk layout)
-    double* sbv = av + Np;          // Sigma_b[band(i)]                         (chunk layout)
-    double* dadd = sbv + Np;        // sigma_i^2                                (chunk layout)
-    double* cbuf = dadd + Np;       // 2 x broadcast column                     (chunk layout)
-    double* piv = cbuf + 2 * Np;    // pivots                                   (natural)
-    double* abuf = piv + Np;        // residual r, later a = K~^-1 r            (chunk layout)
-    double* pbuf = abuf + Np;       // 2 pivot reciprocals (+2 pad)
+    double* av = tsh + VLEN;        // alpha_band(i), 0 for padding            (chunk layout)
+    double* sbv = av + VLEN;        // Sigma_b[band(i)]                         (chunk layout)
+    double* dadd = sbv + VLEN;      // sigma_i^2                                (chunk layout)
+    double* cbuf = dadd + VLEN;     // 2 x broadcast column                     (chunk layout)
+    double* piv = cbuf + 2 * VLEN;  // pivots                                   (natural)
+    double* abuf = piv + VLEN;      // residual r, later a = K~^-1 r            (chunk layout)
+    double* pbuf = abuf + VLEN;     // 2 pivot reciprocals (+2 pad)
     double* red = pbuf + 4;         // 64 reduction slots
     double* part = red + 64;        // [T][T][8] gradient row-sum partials (gradient only)
     int* bandv = reinterpret_cast<int*>(part + (b.want_grad ? T * T * 8 : 0));  // [Np] natural
@@ -211,7 +220,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
     __syncthreads();   // everyone has read abuf/tsh before cbuf traffic starts (abuf is reused later)
 
     // ---- publish column 0, then N sweep steps ----------------------------------------------------
-    if (active) publish<0>(A, ti, tj, 0, 0, T, cbuf, pbuf, piv);
+    publish<0>(A, ti, tj, 0, 0, T, cbuf, pbuf, piv, active);
     __syncthreads();
     for (int tk = 0; tk < T; ++tk) {
         const int k0 = tk * 8;
@@ -363,7 +372,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
 
 size_t smem_bytes(int T, int want_grad) {
     const int Np = T * TS;
-    size_t doubles = (size_t)Np * 8 + 4 + 64 + (want_grad ? (size_t)T * T * 8 : 0);
+    size_t doubles = (size_t)VLEN * 8 + 4 + 64 + (want_grad ? (size_t)T * T * 8 : 0);
     return doubles * sizeof(double) + (size_t)Np * sizeof(int) + 16;
 }
 
