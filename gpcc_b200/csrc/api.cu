@@ -366,7 +366,11 @@ int gpcc_ctx_create(int ndev, const int* dev_ids, gpcc_ctx** out) {
         CUDA_TRY(cudaGetDeviceProperties(&prop, s.dev));
         if (prop.major < 10) { delete ctx; return fail(-4, "libgpcc_b200 is built for sm_100a (Blackwell B200) only"); }
         CUDA_TRY(cudaSetDevice(s.dev));
-        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        // highest priority: in the tiled path this stream carries the critical pivot/panel chain while the bulk of each
+        // trailing update runs on a low-priority stream (large_path.cu), so pivot CTAs get the next free SM
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi));
         for (auto& q : s.slot) {
             CUDA_TRY(cudaEventCreate(&q.ev0));
             CUDA_TRY(cudaEventCreate(&q.ev1));

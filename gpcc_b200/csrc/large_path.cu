@@ -27,6 +27,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 namespace gpcc {
@@ -64,6 +65,7 @@ struct LargeArgs {
     double* part;       // [B][T][T][BT] gradient row-sum partials
     double* epart;      // [B][ntiles]
     size_t mat_stride;  // doubles per matrix
+    size_t x_parity_stride;   // Xws is double buffered by step parity (look-ahead: update k still reads X_k while panel k+1 writes)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -228,107 +230,131 @@ __global__ void __launch_bounds__(256) assemble_kernel(DevProblem p, EvalBatch b
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pivot: Cholesky + triangular inverse of the 128x128 diagonal block in shared memory (one CTA per matrix)
+// pivot: Cholesky + triangular inverse of the 128x128 diagonal block in shared memory (one CTA per matrix).
+// S is column-major with leading dimension 129 (conflict-free along rows and columns).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, row-major
+constexpr int PLD = BT + 1;
+__device__ __forceinline__ double& SE(double* S, int i, int j) { return S[j * PLD + i]; }
 
 __global__ void __launch_bounds__(256) pivot_kernel(LargeArgs a, int k) {
     extern __shared__ double sh[];
-    double* Lp = sh;                         // packed lower L      (8256 doubles)
-    double* Li = sh + BT * (BT + 1) / 2;     // packed lower Linv
-    double* zz = Li + BT * (BT + 1) / 2;     // [BT]
-    double* rk = zz + BT;                    // [BT]
+    double* S = sh;                    // [BT][PLD]
+    double* zz = S + BT * PLD;         // [BT]
+    double* rk = zz + BT;              // [BT]
+    double* ldiag = rk + BT;           // [BT] diagonal of L
     __shared__ int s_bad;
     const int m = blockIdx.x, tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
     double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(k, k) * TILE_ELEMS;
-    for (int e = tid; e < BT * BT; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        if (c <= r) Lp[pk(r, c)] = tile[tl_off(r, c)];
+    for (int e = tid; e < BT * BT / 2; e += 256) {           // coalesced double2 reads of the tile layout
+        const double2 v = *reinterpret_cast<const double2*>(tile + 2 * e);
+        const int mt = e >> 5, w = e & 31;
+        const int r = (mt >> 4) * 8 + (w >> 2), c = (mt & 15) * 8 + (w & 3) * 2;
+        SE(S, r, c) = (c <= r) ? v.x : 0.0;
+        SE(S, r, c + 1) = (c + 1 <= r) ? v.y : 0.0;
     }
     if (tid < BT) rk[tid] = a.rvec[(size_t)m * a.Np + k * BT + tid];
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    // right-looking Cholesky, column by column
+    // ---- right-looking Cholesky: 2 barriers per column, 16x16 thread grid over the trailing block ----
     for (int j = 0; j < BT; ++j) {
-        const double d = Lp[pk(j, j)];
-        if (!(d > 0.0)) { if (tid == 0 && s_bad == 0) s_bad = j + 1; }
-        const double s = sqrt(d), inv = 1.0 / s;
+        __syncthreads();                                   // trailing update of column j-1 is complete
+        const double d = SE(S, j, j);
+        if (!(d > 0.0) && tid == 0 && s_bad == 0) s_bad = j + 1;
+        const double sq = sqrt(d), inv = 1.0 / sq;
+        if (tid > j && tid < BT) SE(S, tid, j) *= inv;    // nobody reads column j (below the diagonal) in this phase
         __syncthreads();
-        if (tid == 0) Lp[pk(j, j)] = s;
-        for (int i = j + 1 + tid; i < BT; i += 256) Lp[pk(i, j)] *= inv;
-        __syncthreads();
-        const int nrem = BT - j - 1;
-        for (int e = tid; e < nrem * nrem; e += 256) {
-            const int ii = e / nrem, cc = e - ii * nrem;
-            if (cc <= ii) {
-                const int i = j + 1 + ii, c = j + 1 + cc;
-                Lp[pk(i, c)] = fma(-Lp[pk(i, j)], Lp[pk(c, j)], Lp[pk(i, c)]);
-            }
-        }
-        __syncthreads();
-    }
-    // Linv: thread j solves L x = e_j (column j of the inverse)
-    if (tid < BT) {
-        const int j = tid;
-        Li[pk(j, j)] = 1.0 / Lp[pk(j, j)];
-        for (int i = j + 1; i < BT; ++i) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four chains: the FMA latency, not the pipe, bounds this loop
-            int q = j;
-            for (; q + 3 < i; q += 4) {
-                s0 = fma(Lp[pk(i, q)], Li[pk(q, j)], s0);
-                s1 = fma(Lp[pk(i, q + 1)], Li[pk(q + 1, j)], s1);
-                s2 = fma(Lp[pk(i, q + 2)], Li[pk(q + 2, j)], s2);
-                s3 = fma(Lp[pk(i, q + 3)], Li[pk(q + 3, j)], s3);
-            }
-            for (; q < i; ++q) s0 = fma(Lp[pk(i, q)], Li[pk(q, j)], s0);
-            Li[pk(i, j)] = -((s0 + s1) + (s2 + s3)) / Lp[pk(i, i)];
+        if (tid == j) { SE(S, j, j) = sq; ldiag[j] = sq; } // the trailing phase never reads S(j,j)
+        for (int i = j + 1 + ty; i < BT; i += 16) {
+            const double lij = SE(S, i, j);
+            for (int c = j + 1 + tx; c <= i; c += 16) SE(S, i, c) = fma(-lij, SE(S, c, j), SE(S, i, c));
         }
     }
     __syncthreads();
+    if (!a.sweep) {   // forward mode: the diagonal tile keeps the Cholesky factor (upper part zero)
+        for (int e = tid; e < BT * BT / 2; e += 256) {
+            const int mt = e >> 5, w = e & 31;
+            const int r = (mt >> 4) * 8 + (w >> 2), c = (mt & 15) * 8 + (w & 3) * 2;
+            *reinterpret_cast<double2*>(tile + 2 * e) = make_double2(SE(S, r, c), SE(S, r, c + 1));
+        }
+    }
+    // ---- in-place inverse of the lower-triangular factor, last column first (dtrti2, lower) ----
+    // two threads per row share each dot product
+    {
+        const int i = tid >> 1, half = tid & 1;
+        for (int j = BT - 1; j >= 0; --j) {
+            double x = 0.0;
+            if (i > j) {
+                double s0 = 0.0, s1 = 0.0;
+                int q = j + 1 + half;
+                for (; q + 2 <= i; q += 4) {
+                    s0 = fma(SE(S, i, q), SE(S, q, j), s0);
+                    s1 = fma(SE(S, i, q + 2), SE(S, q + 2, j), s1);
+                }
+                for (; q <= i; q += 2) s0 = fma(SE(S, i, q), SE(S, q, j), s0);
+                x = s0 + s1;
+            }
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            const double ajj = 1.0 / SE(S, j, j);
+            __syncthreads();
+            if (half == 0) {
+                if (i > j) SE(S, i, j) = -ajj * x;
+                else if (i == j) SE(S, j, j) = ajj;
+            }
+            __syncthreads();
+        }
+    }
     // z = Linv r_k ; quad += z'z ; logdet += 2 sum log L_jj
     if (tid < BT) {
-        double s = 0.0;
-        for (int q = 0; q <= tid; ++q) s = fma(Li[pk(tid, q)], rk[q], s);
-        zz[tid] = s;
+        double s0 = 0.0;
+        for (int q = 0; q <= tid; ++q) s0 = fma(SE(S, tid, q), rk[q], s0);
+        zz[tid] = s0;
     }
     __syncthreads();
     if (tid == 0) {
         double q = 0.0, ld = 0.0;
-        for (int i = 0; i < BT; ++i) { q = fma(zz[i], zz[i], q); ld += log(Lp[pk(i, i)]); }
+        for (int i = 0; i < BT; ++i) { q = fma(zz[i], zz[i], q); ld += log(ldiag[i]); }
         a.scal[(size_t)m * 4 + 0] += 2.0 * ld;
         a.scal[(size_t)m * 4 + 1] += q;
         if (s_bad && a.info[m] == 0) a.info[m] = k * BT + s_bad;
     }
     if (tid < BT) a.zk[(size_t)m * BT + tid] = zz[tid];
-    // Linv in panel layout: element (c, kk) = Linv[c][kk]
+    // Linv in panel layout: element (c, kk) = Linv[c][kk]  (coalesced: consecutive threads write consecutive doubles)
     double* gL = a.Linv + (size_t)m * TILE_ELEMS;
-    for (int e = tid; e < BT * BT; e += 256) {
-        const int c = e >> 7, kk = e & 127;
-        gL[pl_off(c, kk)] = (kk <= c) ? Li[pk(c, kk)] : 0.0;
+    for (int o = tid; o < TILE_ELEMS; o += 256) {
+        const int c4 = o & 3, r8 = (o >> 2) & 7, ro = (o >> 5) & 15, k4 = o >> 9;
+        gL[o] = SE(S, ro * 8 + r8, k4 * 4 + c4);
     }
     if (a.sweep) {
-        // r_k <- Linv' z  (= D^-1 r_k)
-        if (tid < BT) {
-            double s = 0.0;
-            for (int q = tid; q < BT; ++q) s = fma(Li[pk(q, tid)], zz[q], s);
-            a.rvec[(size_t)m * a.Np + k * BT + tid] = s;
+        if (tid < BT) {   // r_k <- Linv' z  (= D^-1 r_k)
+            double s0 = 0.0;
+            for (int q = tid; q < BT; ++q) s0 = fma(SE(S, q, tid), zz[q], s0);
+            a.rvec[(size_t)m * a.Np + k * BT + tid] = s0;
         }
-        // Dinv = Linv' Linv ; A_kk <- -Dinv
+        // Dinv = Linv' Linv as an 8x8 register tile per thread (rows ty+16a, cols tx+16b) ; A_kk <- -Dinv
+        double acc[8][8];
+#pragma unroll
+        for (int p_ = 0; p_ < 8; ++p_)
+#pragma unroll
+            for (int q_ = 0; q_ < 8; ++q_) acc[p_][q_] = 0.0;
+        for (int q = 0; q < BT; ++q) {
+            double lr[8], lc[8];
+#pragma unroll
+            for (int p_ = 0; p_ < 8; ++p_) { lr[p_] = SE(S, q, ty + 16 * p_); lc[p_] = SE(S, q, tx + 16 * p_); }
+#pragma unroll
+            for (int p_ = 0; p_ < 8; ++p_)
+#pragma unroll
+                for (int q_ = 0; q_ < 8; ++q_) acc[p_][q_] = fma(lr[p_], lc[q_], acc[p_][q_]);
+        }
         double* gD = a.Dinv + (size_t)m * TILE_ELEMS;
-        for (int e = tid; e < BT * BT; e += 256) {
-            const int r = e >> 7, c = e & 127;
-            const int q0 = r > c ? r : c;
-            double s = 0.0;
-            for (int q = q0; q < BT; ++q) s = fma(Li[pk(q, r)], Li[pk(q, c)], s);
-            gD[pl_off(r, c)] = s;
-            tile[tl_off(r, c)] = -s;
-        }
-    } else {
-        // forward mode: leave the Cholesky factor in the diagonal tile
-        for (int e = tid; e < BT * BT; e += 256) {
-            const int r = e >> 7, c = e & 127;
-            tile[tl_off(r, c)] = (c <= r) ? Lp[pk(r, c)] : 0.0;
-        }
+#pragma unroll
+        for (int p_ = 0; p_ < 8; ++p_)
+#pragma unroll
+            for (int q_ = 0; q_ < 8; ++q_) {
+                const int r = ty + 16 * p_, c = tx + 16 * q_;
+                gD[pl_off(r, c)] = acc[p_][q_];
+                tile[tl_off(r, c)] = -acc[p_][q_];
+            }
     }
 }
 
@@ -381,7 +407,7 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I
     const int ro0 = (warp & 3) * 4, co0 = (warp >> 2) * 8;
     double* mat = a.mats + (size_t)m * a.mat_stride;
     if (which == 0) {
-        double* xo = a.Xws + ((size_t)m * a.T + I) * TILE_ELEMS;
+        double* xo = a.Xws + (size_t)(k & 1) * a.x_parity_stride + ((size_t)m * a.T + I) * TILE_ELEMS;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -442,20 +468,33 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I
 // ---------------------------------------------------------------------------------------------------------------
 // update: A_IJ -= X_I X_J'  for the lower tiles not touching block k (sweep) / beyond block k (forward)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k) {
+// phase 0: every tile; phase 1: only the tiles of block row/column k+1 (what the next pivot and panel need: the
+// look-ahead part, issued on the critical stream); phase 2: all the others (issued on the bulk stream).
+__global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k, int phase) {
     extern __shared__ __align__(128) unsigned char smraw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
     const int m = blockIdx.y;
     const int tix = blockIdx.x;
-    int Ir = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
-    while ((size_t)Ir * (Ir + 1) / 2 > (size_t)tix) --Ir;
-    while ((size_t)(Ir + 1) * (Ir + 2) / 2 <= (size_t)tix) ++Ir;
-    const int Jr = tix - Ir * (Ir + 1) / 2;
+    const int T = a.T, n1 = k + 1;
     int I, J;
-    if (a.sweep) { I = Ir + (Ir >= k); J = Jr + (Jr >= k); }
-    else { I = Ir + k + 1; J = Jr + k + 1; }
-    const double* gA = a.Xws + ((size_t)m * a.T + I) * TILE_ELEMS;
-    const double* gB = a.Xws + ((size_t)m * a.T + J) * TILE_ELEMS;
+    if (phase == 1) {
+        if (a.sweep) {              // (n1, J) for J in [0, n1] \ {k}  (n1 tiles), then (I, n1) for I > n1
+            if (tix < n1) { I = n1; J = tix + (tix >= k); }
+            else { I = n1 + 1 + (tix - n1); J = n1; }
+        } else { I = n1 + tix; J = n1; }
+    } else {
+        int Ir = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+        while ((size_t)Ir * (Ir + 1) / 2 > (size_t)tix) --Ir;
+        while ((size_t)(Ir + 1) * (Ir + 2) / 2 <= (size_t)tix) ++Ir;
+        const int Jr = tix - Ir * (Ir + 1) / 2;
+        const int skip = (phase == 2) ? 2 : 1;       // blocks k (and k+1 in phase 2) are left out
+        if (a.sweep) { I = Ir + (Ir >= k ? skip : 0); J = Jr + (Jr >= k ? skip : 0); }
+        else { I = Ir + k + skip; J = Jr + k + skip; }
+    }
+    (void)T;
+    const double* xw = a.Xws + (size_t)(k & 1) * a.x_parity_stride;
+    const double* gA = xw + ((size_t)m * a.T + I) * TILE_ELEMS;
+    const double* gB = xw + ((size_t)m * a.T + J) * TILE_ELEMS;
     double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ro0 = (warp & 3) * 4, co0 = (warp >> 2) * 8;
@@ -633,11 +672,17 @@ struct LargeImpl {
            *scal = nullptr, *tsh = nullptr, *av = nullptr, *part = nullptr, *epart = nullptr;
     int* info = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t bulk = nullptr;                 // second stream: the bulk of each trailing update (look-ahead)
+    cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_bulk[2] = {nullptr, nullptr}, ev_join = nullptr;
     bool attr_set = false;
     void release() {
         for (double* p : {mats, Pws, Xws, Linv, Dinv, rvec, zk, scal, tsh, av, part, epart}) if (p) cudaFree(p);
         if (info) cudaFree(info);
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : ev_panel) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : ev_bulk) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
+        if (bulk) { cudaStreamDestroy(bulk); bulk = nullptr; }
         mats = Pws = Xws = Linv = Dinv = rvec = zk = scal = tsh = av = part = epart = nullptr;
         info = nullptr;
         B = 0;
@@ -654,7 +699,7 @@ cudaError_t ensure(LargeImpl& w, int N, int want_B) {
     size_t free_b = 0, total_b = 0;
     cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
     if (e != cudaSuccess) return e;
-    const size_t per = (w.mat_stride + 2 * (size_t)T * TILE_ELEMS + 2 * TILE_ELEMS + (size_t)T * T * BT + ntiles + 4 * (size_t)w.Np) * sizeof(double);
+    const size_t per = (w.mat_stride + 3 * (size_t)T * TILE_ELEMS + 2 * TILE_ELEMS + (size_t)T * T * BT + ntiles + 4 * (size_t)w.Np) * sizeof(double);
     int B = want_B;
     while (B > 1 && (size_t)B * per > free_b / 2) B /= 2;
     if ((size_t)B * per > free_b) return cudaErrorMemoryAllocation;
@@ -662,7 +707,7 @@ cudaError_t ensure(LargeImpl& w, int N, int want_B) {
 #define ALLOC(ptr, n) if ((e = cudaMalloc(&ptr, (size_t)(n) * sizeof(*ptr))) != cudaSuccess) return e;
     ALLOC(w.mats, (size_t)B * w.mat_stride)
     ALLOC(w.Pws, (size_t)B * T * TILE_ELEMS)
-    ALLOC(w.Xws, (size_t)B * T * TILE_ELEMS)
+    ALLOC(w.Xws, (size_t)2 * B * T * TILE_ELEMS)
     ALLOC(w.Linv, (size_t)B * TILE_ELEMS)
     ALLOC(w.Dinv, (size_t)B * TILE_ELEMS)
     ALLOC(w.rvec, (size_t)B * w.Np)
@@ -675,6 +720,12 @@ cudaError_t ensure(LargeImpl& w, int N, int want_B) {
     ALLOC(w.info, (size_t)B)
 #undef ALLOC
     for (auto& ev : w.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
+    for (auto& ev : w.ev_panel) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (auto& ev : w.ev_bulk) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    int prio_lo = 0, prio_hi = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&w.bulk, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -687,10 +738,11 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, La
     a.mode_postb = b.mode_postb;
     a.mats = w.mats; a.Pws = w.Pws; a.Xws = w.Xws; a.Linv = w.Linv; a.Dinv = w.Dinv; a.rvec = w.rvec; a.zk = w.zk;
     a.scal = w.scal; a.info = w.info; a.tsh = w.tsh; a.av = w.av; a.part = w.part; a.epart = w.epart; a.mat_stride = w.mat_stride;
+    a.x_parity_stride = (size_t)w.B * w.T * TILE_ELEMS;
     const int T = w.T;
     const int ntiles = T * (T + 1) / 2;
     const size_t gemm_smem = sizeof(GemmSmem) + 128;
-    const size_t pivot_smem = (size_t)(BT * (BT + 1) + 2 * BT) * sizeof(double);
+    const size_t pivot_smem = (size_t)(BT * PLD + 3 * BT) * sizeof(double);
     if (!w.attr_set) {
         cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
         cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
@@ -703,18 +755,45 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, La
     assemble_kernel<KID><<<dim3(ntiles, nb), 256, 0, st>>>(p, b, e0, a);
     launches += 2;
     if (profile) cudaEventRecord(w.ev[1], st);
+    // Look-ahead schedule on two streams.  Critical stream `st`: pivot_k, gather_k, panel_k, then the part of update k
+    // that touches block row/column k+1, so that pivot/gather/panel of step k+1 start while the bulk stream is still
+    // busy with the rest of update k (the pivot kernel occupies one SM per matrix; without look-ahead the other SMs idle).
+    static const bool lookahead = !(getenv("GPCC_LARGE_NO_LOOKAHEAD"));
+    bool bulk_pending[2] = {false, false};
     for (int k = 0; k < T; ++k) {
         pivot_kernel<<<nb, 256, pivot_smem, st>>>(a, k);
         ++launches;
         const int I0 = a.sweep ? 0 : k + 1;
         const int nI = a.sweep ? T - 1 : T - 1 - k;
-        if (nI > 0) {
-            gather_kernel<<<dim3(nI, nb), 256, 0, st>>>(a, k, I0);
-            panel_kernel<<<dim3(nI, nb, a.sweep ? 2 : 1), 256, gemm_smem, st>>>(a, k, I0);
-            update_kernel<<<dim3(nI * (nI + 1) / 2, nb), 256, gemm_smem, st>>>(a, k);
-            launches += 3;
+        if (nI <= 0) continue;
+        gather_kernel<<<dim3(nI, nb), 256, 0, st>>>(a, k, I0);
+        panel_kernel<<<dim3(nI, nb, a.sweep ? 2 : 1), 256, gemm_smem, st>>>(a, k, I0);
+        launches += 2;
+        const bool has_next = (k + 1 < T);
+        const int n_crit = a.sweep ? T - 1 : T - 1 - k;                 // tiles of block row/column k+1
+        const int n_rest_side = a.sweep ? T - 2 : T - 2 - k;
+        const int n_rest = n_rest_side > 0 ? n_rest_side * (n_rest_side + 1) / 2 : 0;
+        if (!lookahead || !has_next) {
+            if (bulk_pending[(k + 1) & 1]) { cudaStreamWaitEvent(st, w.ev_bulk[(k + 1) & 1], 0); bulk_pending[(k + 1) & 1] = false; }
+            update_kernel<<<dim3(nI * (nI + 1) / 2, nb), 256, gemm_smem, st>>>(a, k, 0);
+            ++launches;
+            continue;
+        }
+        cudaEventRecord(w.ev_panel[k & 1], st);
+        // the critical tiles were last written by the bulk part of update k-1
+        if (bulk_pending[(k + 1) & 1]) { cudaStreamWaitEvent(st, w.ev_bulk[(k + 1) & 1], 0); bulk_pending[(k + 1) & 1] = false; }
+        update_kernel<<<dim3(n_crit, nb), 256, gemm_smem, st>>>(a, k, 1);
+        ++launches;
+        if (n_rest > 0) {
+            cudaStreamWaitEvent(w.bulk, w.ev_panel[k & 1], 0);
+            update_kernel<<<dim3(n_rest, nb), 256, gemm_smem, w.bulk>>>(a, k, 2);
+            cudaEventRecord(w.ev_bulk[k & 1], w.bulk);
+            bulk_pending[k & 1] = true;
+            ++launches;
         }
     }
+    for (int q = 0; q < 2; ++q)
+        if (bulk_pending[q]) cudaStreamWaitEvent(st, w.ev_bulk[q], 0);
     if (profile) cudaEventRecord(w.ev[2], st);
     if (b.want_grad) {
         gradreduce_kernel<KID><<<dim3(ntiles, nb), 256, 0, st>>>(b, e0, a);
