@@ -141,6 +141,15 @@ struct LbfgsState {
             tlo = t;
             t = std::isinf(thi) ? 2.0 * t : 0.5 * (tlo + thi);
         } else {
+            // The objective carries ~1e-13 relative rounding noise.  Once the decrease the model predicts for this step is
+            // below that noise, Armijo can no longer be verified and further backtracking only burns evaluations: the
+            // point is converged to within the noise (remaining improvement <= |t g'd|, far below the 1e-6 target).
+            const double noise = 4e-13 * std::fmax(1.0, std::fabs(f));
+            if (ok && std::isfinite(ft) && std::fabs(ft - f) <= noise && -t * gd0 <= noise) {
+                if (have_fb && fb_f < f) { accept(fb_x, fb_f, fb_g, o, hist); if (status == RUNNING) status = CONVERGED; return; }
+                status = CONVERGED;
+                return;
+            }
             thi = t;
             double tn = 0.5 * (tlo + thi);
             if (tlo == 0.0 && ok && std::isfinite(ft)) {     // quadratic interpolation through f(0), f'(0), f(t)
