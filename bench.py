@@ -128,7 +128,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the reference's own CPU path (restated: no Julia in this image) on the host cores."""
     if rank != 0:
         return
@@ -146,10 +146,15 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
                              "sample": "%d of %d candidates (evenly spaced over the grid) per step, one candidate per task, 1 BLAS thread per worker" % (ns, len(delays))},
             "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner) write to fd 1, so fd 1 is
+    # pointed at stderr for the duration of the run and the JSON line is written to the saved descriptor.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -164,7 +169,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
@@ -237,6 +242,8 @@ def main():
             e1[i].record()
             wall += time.perf_counter() - t0
             barrier()
+        if os.environ.get("GPCC_BENCH_VERBOSE"):
+            sys.stderr.write("rank %d %s per-step ms: %s\n" % (rank, fn.__name__, ["%.0f" % a.elapsed_time(b) for a, b in zip(e0, e1)]))
         dev_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
         tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -246,7 +253,7 @@ def main():
     for _ in range(warmup):
         step_resident()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("GPCC_BENCH_NO_SAMPLER"):
         sampler.start()
     # count launches / kernel time per timed step through the library's own CUDA-event statistics
     kstats = []
@@ -350,7 +357,8 @@ def main():
         except Exception as e:      # never lose the headline line over the side measurement
             line["also"]["cfg4"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,6 +12,7 @@ namespace gpcc {
 
 constexpr int LBFGS_MAXN = 9;    // L+1 <= GPCC_MAX_BANDS+1
 constexpr int LBFGS_MAXM = 16;
+constexpr double STEP_CAP = 2.0;   // max |delta theta_i| per L-BFGS iteration
 
 struct LbfgsOptions {
     int max_iter = 1000;
@@ -28,7 +29,7 @@ struct LbfgsState {
     int iters = 0, nfev = 0;
     double x[LBFGS_MAXN], g[LBFGS_MAXN], f = 0.0;
     double d[LBFGS_MAXN], xt[LBFGS_MAXN];
-    double t = 1.0, tlo = 0.0, thi = 0.0, gd0 = 0.0;
+    double t = 1.0, tlo = 0.0, thi = 0.0, gd0 = 0.0, tcap = 0.0;
     int ls_trials = 0;
     bool have_fb = false;              // best Armijo point seen in this line search (fallback)
     double fb_x[LBFGS_MAXN], fb_g[LBFGS_MAXN], fb_f = 0.0;
@@ -90,6 +91,13 @@ struct LbfgsState {
             const double gn = std::sqrt(dot(g, g, n));
             t = std::fmin(1.0, 1.0 / gn);
         }
+        // Cap the step at STEP_CAP units of the unconstrained parameters per iteration.  theta lives on the softplus /
+        // logistic scale: a jump of many units lands where the transforms saturate (alpha -> floor, rho -> rhomin), their
+        // Jacobians vanish and a gradient method crawls for hundreds of iterations in a degenerate basin.
+        double dmax = 0.0;
+        for (int i = 0; i < n; ++i) dmax = std::fmax(dmax, std::fabs(d[i]));
+        tcap = dmax > 0.0 ? STEP_CAP / dmax : std::numeric_limits<double>::infinity();
+        t = std::fmin(t, tcap);
         tlo = 0.0;
         thi = std::numeric_limits<double>::infinity();
         ls_trials = 0;
@@ -133,13 +141,14 @@ struct LbfgsState {
         if (armijo) {
             const double gtd = dot(gt, d, n);
             if (gtd >= c2 * gd0) { accept(xt, ft, gt, o, hist); return; }   // weak Wolfe holds
+            if (std::isinf(thi) && t >= tcap) { accept(xt, ft, gt, o, hist); return; }   // sufficient decrease at the step cap
             if (!have_fb || ft < fb_f) {
                 have_fb = true; fb_f = ft;
                 std::memcpy(fb_x, xt, n * sizeof(double));
                 std::memcpy(fb_g, gt, n * sizeof(double));
             }
             tlo = t;
-            t = std::isinf(thi) ? 2.0 * t : 0.5 * (tlo + thi);
+            t = std::isinf(thi) ? std::fmin(2.0 * t, tcap) : 0.5 * (tlo + thi);
         } else {
             // The objective carries ~1e-13 relative rounding noise.  Once the decrease the model predicts for this step is
             // below that noise, Armijo can no longer be verified and further backtracking only burns evaluations: the

@@ -13,7 +13,7 @@ theta0 = gpcc_b200.initial_solutions(y, 1, 1, 5, 0.1, 300.0)[0][0]
 ref = p.fit_batch(delays, theta0, iterations=1000, rhomin=0.1, rhomax=300.0, gtol=1e-9, ftol=1e-15)
 print("ref: mean nfev %.1f max %d iters %.1f status %s" % (ref["nfev"].mean(), ref["nfev"].max(), ref["iters"].mean(), np.bincount(ref["info"] + 1)))
 post_ref = gpcc_b200.getprobabilities(ref["loglikel"], ctx=ctx)
-for gtol, ftol in [(1e-7, 1e-13), (1e-6, 1e-13), (1e-5, 1e-13), (1e-6, 1e-12), (1e-5, 1e-12), (1e-5, 1e-11), (1e-4, 1e-12)]:
+for gtol, ftol in [(1e-7, 1e-13)]:
     t0 = time.time()
     r = p.fit_batch(delays, theta0, iterations=1000, rhomin=0.1, rhomax=300.0, gtol=gtol, ftol=ftol)
     dt = time.time() - t0
