@@ -258,16 +258,25 @@ def main():
     # count launches / kernel time per timed step through the library's own CUDA-event statistics
     kstats = []
 
+    phase_ms = []
+
     def step_resident_counted():
-        problem.ctx.set_profiling(True)
+        t0 = time.perf_counter()
         res = problem.fit_batch(delays, theta0, iterations=ITERATIONS, rhomin=RHOMIN, rhomax=RHOMAX)
+        t1 = time.perf_counter()
         kstats.append(ctx.stats())
         full = gather_strided(torch.from_numpy(res["loglikel"]).to(dev), M_total, rank, world)
-        post = ctx.getprobabilities(full.cpu().numpy())
+        host_ll = full.cpu().numpy()
+        t2 = time.perf_counter()
+        post = ctx.getprobabilities(host_ll)
+        t3 = time.perf_counter()
+        phase_ms.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, kstats[-1]["ms_eval_kernels"]))
         state.update(res=res, post=post)
         return post
 
     ms_step, wall_ms = timed(step_resident_counted, args.steps)
+    if os.environ.get("GPCC_BENCH_VERBOSE"):
+        sys.stderr.write("rank %d phases (fit, allgather, posterior, fit-kernel) ms: %s\n" % (rank, [tuple(round(v) for v in p_) for p_ in phase_ms]))
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)

@@ -387,6 +387,7 @@ int gpcc_ctx_destroy(gpcc_ctx* ctx) {
     for (auto& s : ctx->ds) {
         cudaSetDevice(s.dev);
         for (auto& q : s.slot) {
+            s.post_ll.release(); s.post_prior.release(); s.post_out.release();
             q.delays.release(); q.alpha.release(); q.rho.release(); q.ll.release(); q.grad.release(); q.info.release();
             if (q.ev0) cudaEventDestroy(q.ev0);
             if (q.ev1) cudaEventDestroy(q.ev1);
@@ -638,16 +639,21 @@ int gpcc_getprobabilities(gpcc_ctx* ctx, int M, const double* loglik, const doub
     if (M < 1) return fail(-2, "M < 1");
     DeviceState& s = ctx->ds[0];
     CUDA_TRY(cudaSetDevice(s.dev));
-    double *d_ll = nullptr, *d_pr = nullptr, *d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_ll, M * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&d_out, M * sizeof(double)));
-    if (logprior) CUDA_TRY(cudaMalloc(&d_pr, M * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(d_ll, loglik, M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    if (logprior) CUDA_TRY(cudaMemcpyAsync(d_pr, logprior, M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(posterior_launch(M, d_ll, d_pr, d_out, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(out_post, d_out, M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    // persistent buffers: cudaMalloc/cudaFree serialise against every other context on the box (and stall for hundreds
+    // of milliseconds when several ranks with NCCL peer mappings hit them at once), so the hot path never calls them
+    CUDA_TRY(s.post_ll.reserve(M));
+    CUDA_TRY(s.post_out.reserve(M));
+    if (logprior) CUDA_TRY(s.post_prior.reserve(M));
+    std::memcpy(s.post_ll.h, loglik, (size_t)M * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(s.post_ll.d, s.post_ll.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    if (logprior) {
+        std::memcpy(s.post_prior.h, logprior, (size_t)M * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(s.post_prior.d, s.post_prior.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    }
+    CUDA_TRY(posterior_launch(M, s.post_ll.d, logprior ? s.post_prior.d : nullptr, s.post_out.d, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.post_out.h, s.post_out.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
-    cudaFree(d_ll); cudaFree(d_out); if (d_pr) cudaFree(d_pr);
+    std::memcpy(out_post, s.post_out.h, (size_t)M * sizeof(double));
     return 0;
 }
 

@@ -59,6 +59,7 @@ struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
     EvalSlot slot[2];
+    DevBuf<double> post_ll, post_prior, post_out;   // persistent staging of the posterior kernel (no cudaMalloc/cudaFree per call)
     LargeWorkspace large;     // tiled large-N path (large_path.cu)
     // per-call statistics (profiling)
     double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
