@@ -93,26 +93,23 @@ __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, in
     // running the generic update with the multiplier (1 - 1/d) in that column writes c - c (1 - 1/d) = c/d without
     // any extra instruction (relative error eps*d in entries of the inverse only; pivots, log-det and the
     // quadratic form never read the swept region).
+    // Row k of its owner tiles must become c * (1/d) as well: there the registers hold c and the row multiplier is the
+    // pivot d itself, so using (d - 1) instead gives c - (d - 1) c/d = c/d.  Only the diagonal element needs a fix.
     const bool own_col = (tj == tk), own_row = (ti == tk);
-    const double vkk = v[KK];
     if (own_col) v[KK] = 1.0 - pr;
 #pragma unroll
     for (int part = 0; part < 4; ++part) {   // rows two at a time: keeps only a pair of broadcast values live
-        const double2 x = *reinterpret_cast<const double2*>(cb + part * CS + 2 * ti);
+        double2 x = *reinterpret_cast<const double2*>(cb + part * CS + 2 * ti);
+        if (part == (KK >> 1) && own_row) {
+            if (KK & 1) x.y -= 1.0; else x.x -= 1.0;
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             A[2 * part][c] = fma(-x.x, v[c], A[2 * part][c]);
             A[2 * part + 1][c] = fma(-x.y, v[c], A[2 * part + 1][c]);
         }
     }
-    v[KK] = vkk;
-    if (__any_sync(0xffffffffu, own_row)) {
-        if (own_row) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) A[KK][c] = v[c];
-            if (own_col) A[KK][KK] = -pr;
-        }
-    }
+    if (own_col && own_row) A[KK][KK] = -pr;
     const int kn = k + 1;
     if (kn < N) {
         double* nb = cbuf + (kn & 1) * VLEN;
