@@ -288,3 +288,61 @@ def test_cfg4_size_properties(ctx):
     lm, _ = p.loglik_batch(delays[:1], alpha[:1] - h * v[:3], rho[:1] - h * v[3])
     fd = (lp[0] - lm[0]) / (2 * h)
     assert abs(fd - grad[0] @ v) / abs(fd) < 1e-5
+
+
+# ---- edge cases of the batched entry points ---------------------------------------------------------------------
+def test_single_band_and_eight_bands(ctx):
+    # L = 1 is the reference's `singlegp` (src/util.jl:74-78); L = 8 is GPCC_MAX_BANDS
+    for nper, kernel in (([25], "matern32"), ([9, 8, 7, 6, 9, 8, 7, 6], "OU")):
+        t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=11, span=15.0)
+        L = len(nper)
+        op, p = oracle.Problem(t, y, s, kernel), Problem(t, y, s, kernel, ctx)
+        rg = np.random.default_rng(4)
+        delays = np.zeros((5, L)); delays[:, 1:] = rg.uniform(-3, 6, (5, L - 1))
+        alpha, rho = rg.uniform(0.5, 2.0, (5, L)), rg.uniform(0.5, 6.0, 5)
+        ll, grad, info = p.loglik_batch(delays, alpha, rho, want_grad=True)
+        for m in range(5):
+            rl, rgd = op.loglik_grad(delays[m], alpha[m], rho[m])
+            assert abs(ll[m] - rl) / abs(rl) < LL_RTOL and np.max(np.abs(grad[m] - rgd)) / np.max(np.abs(rgd)) < GRAD_RTOL
+        th = gpcc_b200.initial_solutions(y, 2, 1, 3, 0.1, 50.0)[0][0]
+        r = p.fit_batch(delays[:2], th, iterations=200, rhomin=0.1, rhomax=50.0)
+        for m in range(2):
+            o = oracle.gpcc(t, y, s, kernel=kernel, delays=delays[m], iterations=200, rhomin=0.1, rhomax=50.0, theta0=th[None], optimizer="lbfgs")
+            assert r["loglikel"][m] >= o[0] - FIT_ATOL      # same optimum or a better basin
+    with pytest.raises(gpcc_b200.GpccError):
+        Problem([np.arange(3.0)] * 9, [np.arange(3.0)] * 9, [np.ones(3)] * 9, "OU", ctx)     # more than GPCC_MAX_BANDS
+
+
+def test_large_batches_are_chunked_consistently(ctx):
+    """More evaluations than one staging chunk (2^18): results must not depend on where the chunk boundaries fall."""
+    t, y, s, d = gpcc_b200.synthetic_bands([7, 2, 13], seed=6, span=10.0)
+    p = Problem(t, y, s, "OU", ctx)
+    M = (1 << 18) + 1234
+    rg = np.random.default_rng(8)
+    delays = np.zeros((M, 3)); delays[:, 1:] = rg.uniform(0, 5, (M, 2))
+    alpha, rho = rg.uniform(0.3, 3.0, (M, 3)), rg.uniform(0.2, 50.0, M)
+    ll, info = p.loglik_batch(delays, alpha, rho)
+    pick = np.r_[0:50, (1 << 18) - 25:(1 << 18) + 25, M - 50:M]
+    ll_s, _ = p.loglik_batch(delays[pick], alpha[pick], rho[pick])
+    assert np.array_equal(ll[pick], ll_s) and np.all(info == 0)
+    op = oracle.Problem(t, y, s, "OU")
+    for m in (0, 1 << 18, M - 1):
+        assert abs(ll[m] - op.loglik(delays[m], alpha[m], rho[m])) / abs(ll[m]) < LL_RTOL
+    # a fitted grid with 60 000 candidates: screening runs in several chunks (2^18 / P candidates each)
+    th = gpcc_b200.initial_solutions(y, 1, 1, 5, 0.1, 100.0)[0][0]
+    Mf = 60000
+    r = p.grid_posterior(delays[:Mf], th, iterations=50, rhomin=0.1, rhomax=100.0)
+    r2 = p.fit_batch(delays[Mf - 100:Mf], th, iterations=50, rhomin=0.1, rhomax=100.0)
+    assert np.array_equal(r["loglikel"][Mf - 100:], r2["loglikel"]) and abs(r["posterior"].sum() - 1.0) < 1e-10
+
+
+def test_prior_with_minus_infinity_and_iteration_cap_zero(ctx):
+    g = load_golden("fit_cfg1_cfg2")
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    delays = np.stack([np.zeros(11), np.linspace(0, 10, 11)], 1)
+    lp = np.zeros(11); lp[[0, 5]] = -np.inf
+    r = p.grid_posterior(delays, g["theta0"], iterations=1000, rhomin=0.1, rhomax=300.0, logprior=lp)
+    assert r["posterior"][0] == 0.0 and r["posterior"][5] == 0.0 and abs(r["posterior"].sum() - 1.0) < 1e-12
+    r0 = p.fit_batch(delays[:3], g["theta0"], iterations=0, rhomin=0.1, rhomax=300.0)     # screening only (:207-209)
+    scr = np.max(np.stack([p.loglik_theta_batch(delays[:3], np.tile(th, (3, 1)), 0.1, 300.0)[0] for th in g["theta0"]]), axis=0)
+    assert np.allclose(r0["loglikel"], scr, rtol=1e-14) and np.all(r0["info"] == 1) and np.all(r0["nfev"] == 5)
