@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -68,7 +69,9 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, d
     q.M = M; q.want_grad = want_grad; q.timed = false;
     if (p->small_path) {
         if (prof) CUDA_TRY(cudaEventRecord(q.ev0, s.stream));
-        CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, s.stream));
+        static const int use_dmma = getenv("GPCC_SMALL_DMMA") ? atoi(getenv("GPCC_SMALL_DMMA")) : 0;
+        if (use_dmma && small_dmma_supports(p->N)) CUDA_TRY(small_dmma_launch(p->pd[di].dp, b, s.stream));
+        else CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, s.stream));
         if (prof) CUDA_TRY(cudaEventRecord(q.ev1, s.stream));
         q.timed = prof;
         s.launches += 1;

@@ -44,6 +44,9 @@ constexpr int SMALL_MAX_T = 25;
 inline bool small_path_supports(int N) { return (N + 1 + SMALL_TILE - 1) / SMALL_TILE <= SMALL_MAX_T; }
 cudaError_t small_sweep_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
 cudaError_t small_sweep_init();   // sets max dynamic shared memory attributes once per device
+// tensor-pipe variant of the fused evaluator (small_dmma.cu)
+bool small_dmma_supports(int N);
+cudaError_t small_dmma_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
 
 
 // ---- large-N path: tiled matrix in HBM, blocked sweep with DMMA trailing updates (large_path.cu) --

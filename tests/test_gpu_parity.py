@@ -346,3 +346,25 @@ def test_prior_with_minus_infinity_and_iteration_cap_zero(ctx):
     r0 = p.fit_batch(delays[:3], g["theta0"], iterations=0, rhomin=0.1, rhomax=300.0)     # screening only (:207-209)
     scr = np.max(np.stack([p.loglik_theta_batch(delays[:3], np.tile(th, (3, 1)), 0.1, 300.0)[0] for th in g["theta0"]]), axis=0)
     assert np.allclose(r0["loglikel"], scr, rtol=1e-14) and np.all(r0["info"] == 1) and np.all(r0["nfev"] == 5)
+
+
+def test_experimental_dmma_fused_kernel_agrees(ctx):
+    """small_dmma.cu (rank-8 block sweep on DMMA for the register-resident sizes) is off by default because it is slower
+    than the DFMA sweep below N~200 (profiles/README.md); it must still be exact.  The switch is read once per process."""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "import gpcc_b200, oracle\n"
+        "from conftest import load_golden\n"
+        "for name in ('loglik_3band_matern32', 'loglik_2band_OU', 'loglik_ragged_OU', 'loglik_3x64_matern52'):\n"
+        "    g = load_golden(name)\n"
+        "    p = gpcc_b200.Problem(g['tb'], g['yb'], g['sb'], g['kernel'])\n"
+        "    ll, grad, info = p.loglik_batch(g['delays'], g['alpha'], g['rho'], want_grad=True)\n"
+        "    assert np.all(info == 0)\n"
+        "    assert np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik'])) < 1e-10, name\n"
+        "    assert np.max(np.abs(grad - g['grad']) / np.max(np.abs(g['grad']), axis=1, keepdims=True)) < 1e-8, name\n"
+        "print('DMMA-OK')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GPCC_SMALL_DMMA="1", PYTHONPATH=os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DMMA-OK" in r.stdout, r.stderr[-2000:]
