@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpcc_b200.so")
+LIB_PATH = os.environ.get("GPCC_B200_LIB") or os.path.join(_HERE, "libgpcc_b200.so")   # override: dev builds only
 
 EXPORTS = [
     "gpcc_version", "gpcc_last_error", "gpcc_ctx_create", "gpcc_ctx_destroy", "gpcc_ctx_set_profiling",

@@ -70,7 +70,11 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, d
     if (p->small_path) {
         if (prof) CUDA_TRY(cudaEventRecord(q.ev0, s.stream));
         static const int use_dmma = getenv("GPCC_SMALL_DMMA") ? atoi(getenv("GPCC_SMALL_DMMA")) : 0;
-        if (use_dmma && small_dmma_supports(p->N)) CUDA_TRY(small_dmma_launch(p->pd[di].dp, b, s.stream));
+        static const int use_block = getenv("GPCC_SMALL_BLOCK") ? atoi(getenv("GPCC_SMALL_BLOCK")) : 0;
+        static const int use_frag = getenv("GPCC_SMALL_FRAG") ? atoi(getenv("GPCC_SMALL_FRAG")) : 0;
+        if (use_frag && small_frag_supports(p->N)) CUDA_TRY(small_frag_launch(p->pd[di].dp, b, s.stream));
+        else if (use_block && small_block_supports(p->N)) CUDA_TRY(small_block_launch(p->pd[di].dp, b, s.stream));
+        else if (use_dmma && small_dmma_supports(p->N)) CUDA_TRY(small_dmma_launch(p->pd[di].dp, b, s.stream));
         else CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, s.stream));
         if (prof) CUDA_TRY(cudaEventRecord(q.ev1, s.stream));
         q.timed = prof;

@@ -44,6 +44,12 @@ constexpr int SMALL_MAX_T = 25;
 inline bool small_path_supports(int N) { return (N + 1 + SMALL_TILE - 1) / SMALL_TILE <= SMALL_MAX_T; }
 cudaError_t small_sweep_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
 cudaError_t small_sweep_init();   // sets max dynamic shared memory attributes once per device
+// blocked (eight pivots per step) form of the fused evaluator (small_block.cu)
+bool small_block_supports(int N);
+cudaError_t small_block_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
+// fragment-layout form: tiles spread over warps, DMMA for panel and update, several matrices per CTA (small_frag.cu)
+bool small_frag_supports(int N);
+cudaError_t small_frag_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
 // tensor-pipe variant of the fused evaluator (small_dmma.cu)
 bool small_dmma_supports(int N);
 cudaError_t small_dmma_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);

@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 import oracle
 from gpcc_b200 import Problem, Context
 ctx = Context(1, profiling=True)
-M = 148 * 64
+M = 148 * int(os.environ.get("GPCC_TS_WAVES", "64"))
 rg = np.random.default_rng(1)
 delays = np.zeros((M, 3)); delays[:, 1:] = rg.uniform(0, 20, (M, 2))
 alpha = rg.uniform(0.5, 3.0, (M, 3)); rho = rg.uniform(0.5, 20, M)
