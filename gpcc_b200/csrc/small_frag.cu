@@ -37,8 +37,8 @@ namespace gpcc {
 
 #ifdef GPCC_FRAG_PROF
 // Dev build only: per-warp timestamps of every block step, kept in shared memory and dumped at exit.
-__device__ long long g_frag_tl[32 * 8 * 12];
-#define PROF_TL(slot) do { if (lane == 0) tlbuf[(k * 8 + (slot)) * 12 + warp + nwarps * gid] = clock64(); } while (0)
+__device__ long long g_frag_tl[32 * 8 * 16];
+#define PROF_TL(slot) do { if (lane == 0) tlbuf[(k * 8 + (slot)) * 16 + warp + (nwarps + 1) * gid] = clock64(); } while (0)
 #else
 #define PROF_TL(slot)
 #endif
@@ -47,8 +47,7 @@ namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 constexpr int MAX_T = 25;      // 8 * 25 = 200 rows (N <= 199 as in small_sweep.cu); 325 tiles = 11 warps
-constexpr int MAX_THREADS = 384;
-constexpr int P3_TILES = 2;   // panel tiles in flight per warp in P3 (registers: the 128 accumulators leave ~40)
+constexpr int MAX_THREADS = 512;   // 16 warps x 128 registers: registers are handed out four warps at a time
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -59,12 +58,24 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // generic pointer from scratch (S2R, S2UR, a dozen dependent IMADs) in front of each access, which is what made every
 // phase of the first version run at ~10 cycles per instruction.
 constexpr int SLOTS = 32;       // tiles per warp ...
-constexpr int REG_SLOTS = 28;   // ... of which this many live in registers (112 of the 168 a thread may use at 12 warps
-                                // per SM); the other four stay in shared memory and take one LDS.128 + STS.128 per block
-                                // step.  With all 32 in registers ptxas keeps four of them in LOCAL memory instead.
+constexpr int REG_SLOTS = 20;   // ... of which this many live in registers (80 of the 128 a thread may use at 16 warps per
+                                // SM); the other twelve stay in shared memory and take one LDS.128 + STS.128 per block step.
+                                // With all 32 in registers ptxas keeps some of them in LOCAL memory instead, which is worse.
+constexpr int CHUNK = 4;        // consecutive tiles (row major over the lower triangle) dealt to a warp at a time: the
+                                // A operand of the update is reloaded only when the tile row changes
 constexpr unsigned O_W = 0, O_WT = 512, O_ZR = 1024, O_MISC = 1088, O_RED = 1152, O_DB = 1280, O_DN = 1792, O_RV = 2304;
-constexpr unsigned O_PIV = O_RV + 1600, O_PARK = O_PIV + 1600, O_TM = O_PARK + REG_SLOTS * 512;
-// O_TM: [nwarps][SLOTS - REG_SLOTS] memory-resident tiles; then Zb, Zn, Cb[0], Cb[1] (pb bytes each)
+constexpr unsigned O_PIV = O_RV + 3072, O_TM = O_PIV + 2048;
+// from O_TM on (sizes depend on the launch): [nwarps][4] memory-resident tiles, [nwarps][32] scan descriptors (8 B),
+// [nwarps][32] update-operand offsets (8 B), then Zb, Zn, Cb[0], Cb[1] (pb = 512 Tpad bytes each)
+__device__ __forceinline__ uint2 lds64u(unsigned a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64u(unsigned a, unsigned x, unsigned y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ double negd(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }   // ALU, not FP64 pipe
 __device__ __forceinline__ double2 lds128(unsigned a) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
@@ -164,13 +175,18 @@ __device__ __forceinline__ void pivot_tile(unsigned gb, int k) {
         for (int q = 0; q < c; ++q) s = fma(A[q][c], r[q], s);
         sts64(gb + O_ZR + c * 8, s);
         qs = fma(s, s, qs);
-#pragma unroll
-        for (int q = 0; q <= c; ++q) {
-            const double w = (q == c) ? A[c][c] : A[q][c];
-            sts64(gb + O_W + (c * 8 + q) * 8, w);     // W  row major (zeros above the diagonal, written once at start)
-            sts64(gb + O_WT + (q * 8 + c) * 8, w);    // W' row major
-        }
     }
+    // W row major and W' row major, in 16-byte pieces (W[c][q] for q < c is A[q][c], W[c][c] = A[c][c], zero above)
+#define W_AT(c, q) ((q) > (c) ? 0.0 : ((q) == (c) ? A[c][c] : A[q][c]))
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int q = 0; q <= c; q += 2) sts128(gb + O_W + (c * 8 + q) * 8, W_AT(c, q), W_AT(c, q + 1));
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int c = q & ~1; c < 8; c += 2) sts128(gb + O_WT + (q * 8 + c) * 8, W_AT(c, q), W_AT(c + 1, q));
+#undef W_AT
     sts64(gb + O_MISC, lds64(gb + O_MISC) + qs);
 }
 
@@ -180,50 +196,50 @@ __device__ __forceinline__ void pivot_tile(unsigned gb, int k) {
 #define TILE_PUT(s, v0, v1) do { if ((s) < REG_SLOTS) { acc[(s) < REG_SLOTS ? (s) : 0][0] = v0; acc[(s) < REG_SLOTS ? (s) : 0][1] = v1; } \
                                  else sts128(tm + ((s) - REG_SLOTS) * 512, v0, v1); } while (0)
 
-// One pass over the tiles of a warp after the trailing update of block step k (kw = k), or before the first step
-// (kw = -1).  Warp-uniform tests only; a tile costs one or two shared-memory accesses per lane:
-//   * tiles of row / column kw take their final values X = C D^-1 from the panel buffer (pivot tile: -D^-1);
-//   * tiles of row / column kw+1 are copied into the next panel buffer; its pivot tile leaves identity rows there
-//     (their X rows become D^-1); when `first`, the pivot tile itself goes to Db (later ones arrive through P3);
-//   * the pivot tile kw+2 is copied, as it stands, to Dn: P3 of step kw+1 finishes it (look-ahead).
-__device__ __forceinline__ void scan_tiles(double (&acc)[REG_SLOTS][2], unsigned tm, int mytile, int kw, unsigned lane16, unsigned lanet,
-                                           unsigned cw, unsigned cn, unsigned gb, bool first) {
-    // lane16 = 16 * lane: this lane's pair inside a row-major tile; lanet = 8 * (lc * 8 + lr): the same pair transposed
-    const int mti = mytile >> 8, mtj = mytile & 255;
-    const int kn = kw + 1, kp = kw + 2;
-    const unsigned mask = __ballot_sync(0xffffffffu, mytile >= 0 && (mti == kw || mtj == kw || mti == kn || mtj == kn || (mti == kp && mtj == kp)));
+// Scan descriptors of block step kw (kw = -1 before the first step), one per tile, written by the lane whose number is
+// the tile's slot: {address to take the final value from, address to copy the tile to} (0 = nothing to do).
+//   * tiles of column kw (and the pivot tile) read X = C D^-1 (pivot: -D^-1) from block ti of the panel buffer, tiles of
+//     row kw from block tj: P3 stores every block in the fragment layout of the tile that will read it;
+//   * tiles of column / row kw+1 are copied to block ti / tj of the next panel buffer, as they are (P3 reads the blocks
+//     that come from row tiles transposed);  the pivot tile kw+2 goes to Dn (look-ahead), and before the first step the
+//     pivot tile 0 goes to Db.
+__device__ __forceinline__ void write_descriptors(unsigned da, int mytile, int kw, unsigned cw, unsigned cn, unsigned gb) {
+    const int mti = mytile >> 8, mtj = mytile & 255, kn = kw + 1, kp = kw + 2;
+    unsigned src = 0, dst = 0;
+    if (mytile >= 0) {
+        if (mtj == kw) src = cw + mti * 512; else if (mti == kw) src = cw + mtj * 512;
+        if (mtj == kn) { if (mti != kn) dst = cn + mti * 512; else if (kw < 0) dst = gb + O_DB; }
+        else if (mti == kn) dst = cn + mtj * 512;
+        else if (mti == kp && mtj == kp) dst = gb + O_DN;
+    }
+    sts64u(da, src, dst);
+}
+// The scan proper: one predicated 16-byte load and one predicated 16-byte store per tile, no branches for the tiles
+// in registers.
+__device__ __forceinline__ void scan_tiles(double (&acc)[REG_SLOTS][2], unsigned tm, unsigned dw, unsigned lane16) {
+    // A warp issues in order and these accesses are ordered among themselves: descriptors are fetched eight at a time,
+    // then the loads they select, then the stores, so that the latencies overlap instead of adding up.
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        if ((mask >> s) & 1u) {
-            const int tt = __shfl_sync(0xffffffffu, mytile, s);
-            const int ti = tt >> 8, tj = tt & 255;
-            double v0, v1;
-            if (tj == kw) {           // column tile: X rows ti*8 + r;  pivot tile: -D^-1
-                const double2 v = lds128(cw + ti * 512 + lane16);
-                const double sg = (ti == kw) ? -1.0 : 1.0;
-                v0 = sg * v.x;
-                v1 = sg * v.y;
-                TILE_PUT(s, v0, v1);
-            } else if (ti == kw) {    // row tile (kw, tj): element (r, c) = X[tj*8 + c][r]
-                v0 = lds64(cw + tj * 512 + lanet);
-                v1 = lds64(cw + tj * 512 + lanet + 64);
-                TILE_PUT(s, v0, v1);
-            } else {
-                TILE_GET(s, v0, v1);
+    for (int g = 0; g < SLOTS; g += 8) {
+        uint2 d[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = lds64u(dw + (g + u) * 8);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int s = g + u;
+            if (s < REG_SLOTS) {
+                if (d[u].x) { const double2 v = lds128(d[u].x + lane16); acc[s < REG_SLOTS ? s : 0][0] = v.x; acc[s < REG_SLOTS ? s : 0][1] = v.y; }
             }
-            if (tj == kn) {
-                if (ti == kn) {       // next pivot tile: identity rows in the panel
-                    const int lr = lane16 >> 6, lc = (lane16 >> 3) & 6;
-                    sts128(cn + kn * 512 + lane16, lr == lc ? 1.0 : 0.0, lr == lc + 1 ? 1.0 : 0.0);
-                    if (first) sts128(gb + O_DB + lane16, v0, v1);
-                } else {              // column tile: panel rows ti*8 + r
-                    sts128(cn + ti * 512 + lane16, v0, v1);
-                }
-            } else if (ti == kn) {    // row tile (kn, tj): panel rows tj*8 + c, entry r
-                sts64(cn + tj * 512 + lanet, v0);
-                sts64(cn + tj * 512 + lanet + 64, v1);
-            } else if (ti == kp && tj == kp) {
-                sts128(gb + O_DN + lane16, v0, v1);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int s = g + u;
+            if (s < REG_SLOTS) {
+                if (d[u].y) sts128(d[u].y + lane16, acc[s < REG_SLOTS ? s : 0][0], acc[s < REG_SLOTS ? s : 0][1]);
+            } else if (d[u].x | d[u].y) {
+                const double2 v = lds128(d[u].x ? d[u].x + lane16 : tm + (s - REG_SLOTS) * 512);
+                if (d[u].x) sts128(tm + (s - REG_SLOTS) * 512, v.x, v.y);
+                if (d[u].y) sts128(d[u].y + lane16, v.x, v.y);
             }
         }
     }
@@ -231,40 +247,53 @@ __device__ __forceinline__ void scan_tiles(double (&acc)[REG_SLOTS][2], unsigned
 
 template <int KID>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int smem_doubles_per_group) {
+small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int hw_per_group, int nmat, int smem_doubles_per_group) {
     extern __shared__ __align__(16) double smem_all[];
     const int N = p.N, L = p.L;
     const int Np = 8 * T;
-    const int gid = (int)threadIdx.x / gthreads;
-    const int tid = (int)threadIdx.x - gid * gthreads;
+    // Hardware warp w runs on scheduler w % 4.  Tile warps take the slots with w % 4 != 3, the helper warp of each matrix
+    // one with w % 4 == 3: its scalar FP64 chain (the pivot factorisation) then never queues behind the 16-cycle DMMAs
+    // of a tile warp, which slows it four-fold (measured).  Slots left over exit at once.
+    const int hwarp = (int)threadIdx.x >> 5, gid = hwarp / hw_per_group, hl = hwarp % hw_per_group;
+    const int ntw = (gthreads >> 5) - 1;
+    int role = ((hl & 3) == 3) ? ((hl == 3) ? ntw : -1) : (hl >> 2) * 3 + (hl & 3);
+    if (role > ntw || ((hl & 3) != 3 && role >= ntw)) role = -1;
     const int e = blockIdx.x * nmat + gid;
-    if (e >= b.M) return;   // whole group leaves: its named barriers are never used
+    if (role < 0 || e >= b.M) return;   // spare slots; a whole group without work: its named barriers are never used
+    const int tid = role * 32 + ((int)threadIdx.x & 31);
     const bool next_group_exists = (gid + 1 < nmat) && (e + 1 < b.M);
     double* smem = smem_all + (size_t)gid * smem_doubles_per_group;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = gthreads >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (gthreads >> 5) - 1;   // tile warps; warp `nwarps` is the helper
+    const bool helper = (warp == nwarps);
     const int ntiles = T * (T + 1) / 2;
     const int lr = lane >> 2, lc = (lane & 3) * 2;   // this lane's row and first column inside a tile
 
-    const unsigned pb = 512u * T;                                   // bytes of one panel buffer
+    const unsigned pb = 512u * Tpad;                                // bytes of one panel buffer (Tpad: T rounded up to 2 nwarps)
     const unsigned gb = (unsigned)__cvta_generic_to_shared(smem);   // shared-window address of this group
-    const unsigned lane16 = 16u * lane, lanet = 8u * (lc * 8 + lr);
+    const unsigned lane16 = 16u * lane;
+    const unsigned ltr = 16u * (lc * 4 + (lr >> 1)) + 8u * (lr & 1);   // this lane's first element in the TRANSPOSED tile (second: + 64)
+    const unsigned odesc = O_TM + (unsigned)nwarps * (SLOTS - REG_SLOTS) * 512, otab = odesc + (unsigned)nwarps * 256;
+    const unsigned ozb = otab + (unsigned)nwarps * 256;
+    const unsigned tm = gb + O_TM + (unsigned)warp * (SLOTS - REG_SLOTS) * 512 + lane16;   // this lane's pair of the warp's first memory tile
+    const unsigned dw = gb + odesc + (unsigned)warp * 256, tw = gb + otab + (unsigned)warp * 256;
     double* Wb = smem + O_W / 8;        // [64] W = L^-1 row major, [64] W' row major
     double* misc = smem + O_MISC / 8;   // [0] quadratic form, [2] info (as int)
     double* red = smem + O_RED / 8;     // [16] warp totals
-    double* rv = smem + O_RV / 8;       // [Np] residual, swept along with the matrix: ends as a = K~^-1 r
+    double* rv = smem + O_RV / 8;       // [8 Tpad] residual, swept along with the matrix: ends as a = K~^-1 r
     double* piv = smem + O_PIV / 8;     // [Np] Schur pivots
-    const unsigned ozb = O_TM + (unsigned)nwarps * (SLOTS - REG_SLOTS) * 512;
-    const unsigned tm = gb + O_TM + (unsigned)warp * (SLOTS - REG_SLOTS) * 512 + lane16;   // this lane's pair of the warp's first memory tile
-    double* Zb = smem + ozb / 8;        // [T][64] Z, then [T][64] -Z, then [2][T][64] panel C / X = C D^-1 (row-major 8x8 per tile row)
+    double* Zb = smem + ozb / 8;        // [Tpad][64] Z, then -Z, then [2][Tpad][64] panel C / X = C D^-1
     double2* stage = reinterpret_cast<double2*>(Zb);   // [nwarps][8][32] fragment staging (assembly, gradient): aliases the panels
-    const size_t panel_doubles = (size_t)4 * T * 64, stage_doubles = (size_t)nwarps * 512;
+    const size_t panel_doubles = (size_t)4 * Tpad * 64, stage_doubles = (size_t)nwarps * 512;
     double* tsh = Zb + (panel_doubles > stage_doubles ? panel_doubles : stage_doubles);   // [Np] shifted times
     double* av = tsh + Np;              // [Np] alpha per point (0 on padding)
     double* sbv = av + Np;              // [Np] Sigma_b per point
     double* dadd = sbv + Np;            // [Np] sigma^2 (1 on padding: identity pivots)
-    double* part = dadd + Np;           // [T][T][8] gradient partials
-    double* partd = part + (b.want_grad ? T * T * 8 : 0);                                  // [T][8]
-    int* bandv = reinterpret_cast<int*>(partd + (b.want_grad ? T * 8 : 0));                // [Np]
+    // [T][T][8] + [T][8] gradient partials: behind the staging buffer inside the (by then idle) panel region when they fit
+    const size_t part_doubles = b.want_grad ? (size_t)T * T * 8 + (size_t)T * 8 : 0;
+    const bool part_aliased = stage_doubles + part_doubles <= panel_doubles;
+    double* part = part_aliased ? Zb + stage_doubles : dadd + Np;
+    double* partd = part + (b.want_grad ? T * T * 8 : 0);
+    int* bandv = reinterpret_cast<int*>(dadd + Np + (part_aliased ? 0 : part_doubles));   // [Np]
 #ifdef GPCC_FRAG_PROF
     long long* tlbuf = reinterpret_cast<long long*>(smem_all + (size_t)nmat * smem_doubles_per_group);
 #endif
@@ -273,7 +302,7 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
     const double rho = b.rho[e];
     const KernParams kp = make_kern_params(KID, rho);
 
-    for (int i = tid; i < Np; i += gthreads) {
+    for (int i = tid; i < 8 * Tpad; i += gthreads) {
         double ts = 0.0, al = 0.0, sb = 0.0, dd = 1.0, r = 0.0;
         int bi = -1 - i;
         if (i < N) {
@@ -284,25 +313,33 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
             dd = p.s2[i];
             r = b.mode_postb ? p.y[i] : p.resid[i];
         }
-        tsh[i] = ts; av[i] = al; sbv[i] = sb; dadd[i] = dd; rv[i] = r; bandv[i] = bi;
+        rv[i] = r;
+        if (i < Np) { tsh[i] = ts; av[i] = al; sbv[i] = sb; dadd[i] = dd; bandv[i] = bi; }
     }
     if (tid < 128) Wb[tid] = 0.0;
     if (tid == 0) misc[0] = 0.0;
-    // slot s of this warp is tile q = s * nwarps + warp (round robin); lane s remembers it for the whole warp
+    // Slot s of this warp is tile q = ((s / CHUNK) * nwarps + warp) * CHUNK + s % CHUNK (chunks of consecutive tiles dealt
+    // round robin); lane s keeps that tile's coordinates for the whole warp and writes its entry of the warp's
+    // update-operand table {512 ti, 512 tj}.
     int mytile = -1;
     {
-        const int q = lane * nwarps + warp;
-        if (q < ntiles) { int a_, b_; tile_of(q, a_, b_); mytile = (a_ << 8) | b_; }
+        const int q = ((lane / CHUNK) * nwarps + warp) * CHUNK + lane % CHUNK;
+        if (!helper && q < ntiles) { int a_, b_; tile_of(q, a_, b_); mytile = (a_ << 8) | b_; }
+        if (!helper) sts64u(tw + lane * 8, mytile < 0 ? 0u : (unsigned)(mytile >> 8) * 512u, mytile < 0 ? 0u : (unsigned)(mytile & 255) * 512u);
     }
-    const unsigned myoffs = mytile < 0 ? 0u : (unsigned)((mytile >> 8) * 512) | ((unsigned)((mytile & 255) * 512) << 16);
+    // bit s: the A operand (tile row) of slot s differs from that of slot s-1
+    const int prevtile = __shfl_up_sync(0xffffffffu, mytile, 1);
+    const unsigned amask = __ballot_sync(0xffffffffu, (mytile >> 8) != (prevtile >> 8)) | 1u;
     group_sync(gid, gthreads);
 
     // ---- assembly, eight tiles at a time through the staging buffer (keeps the exp code out of the unrolled part) ---
     double acc[REG_SLOTS][2];
+    if (!helper)   // (the helper warp has no tiles: its accumulators stay undefined and are never read)
 #pragma unroll
     for (int c = 0; c < SLOTS / 8; ++c) {
         for (int u = 0; u < 8; ++u) {
-            const int q = (c * 8 + u) * nwarps + warp;
+            const int sl = c * 8 + u;
+            const int q = ((sl / CHUNK) * nwarps + warp) * CHUNK + sl % CHUNK;
             double v0 = 0.0, v1 = 0.0;
             if (q < ntiles) {
                 int ti, tj;
@@ -332,60 +369,97 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
     // Matrices of one CTA start one after the other: the next one enters its sweep when this one reaches its first
     // trailing update, so that their serial phases and DMMA streams interleave from then on.
     if (gid > 0) asm volatile("bar.sync %0, %1;" ::"r"(8 + gid), "r"(2 * gthreads) : "memory");
-    scan_tiles(acc, tm, mytile, -1, lane16, lanet, gb + ozb + 2 * pb, gb + ozb + 2 * pb, gb, true);   // panel 0, pivot tile 0 -> Db, pivot tile 1 -> Dn
-    if (warp == 0) {   // tile (0,0) is slot 0 of warp 0
+    if (!helper) {
+        write_descriptors(dw + lane * 8, mytile, -1, 0u, gb + ozb + 2 * pb, gb);   // panel 0, pivot tile 0 -> Db, pivot tile 1 -> Dn
         __syncwarp();
-        if (lane == 0) pivot_tile(gb, 0);
+        scan_tiles(acc, tm, dw, lane16);
     }
-    int pw = (nwarps > 1) ? 1 : 0;   // warp that finishes pivot tile k+1 in P3 of step k: (k+1) % nwarps
+    group_sync(gid, gthreads);
+    if (helper) {
+        // Look-ahead: while the tile warps run the trailing update of step k, the helper warp finishes the next pivot
+        // tile (D - Z Z' with Z = block k+1 of this step's panel, two DMMAs) and ONE of its lanes factors it: Cholesky of
+        // the 8x8 block, W = L^-1, zr = W r_{k+1}.  That chain needs the registers of a whole thread and ~2 k cycles of
+        // dependent FP64 latency; on a warp that also owns tiles it would be the critical path of every step.
+        if (lane == 0) pivot_tile(gb, 0);
+        for (int k = 0; k < T; ++k) {
+            PROF_TL(0);
+            group_sync(gid, gthreads);   // B1
+            PROF_TL(1); PROF_TL(2);
+            group_sync(gid, gthreads);   // B2
+            PROF_TL(3);
+            if (k == 0 && next_group_exists) asm volatile("bar.arrive %0, %1;" ::"r"(8 + gid + 1), "r"(2 * gthreads) : "memory");
+            if (k + 1 < T) {
+                const double2 z = lds128(gb + ozb + (k + 1) * 512 + lane16);
+                double2 d = lds128(gb + O_DN + lane16);
+                dmma884(d.x, d.y, negd(z.x), z.x);
+                dmma884(d.x, d.y, negd(z.y), z.y);
+                sts128(gb + O_DB + lane16, d.x, d.y);
+                __syncwarp();
+                if (lane == 0) pivot_tile(gb, k + 1);
+            }
+            PROF_TL(4); PROF_TL(5); PROF_TL(6);
+        }
+    } else
     for (int k = 0; k < T; ++k) {
         const unsigned cw = gb + ozb + (2 + (k & 1)) * pb, cn = gb + ozb + (3 - (k & 1)) * pb;
         PROF_TL(0);
         group_sync(gid, gthreads);
         PROF_TL(1);
-        // P3: Z = C W', X = Z W, r -= Z zr on DMMA, up to four independent 8-row tiles in flight per warp
+        // P3: Z = C W', X = Z W, r -= Z zr on DMMA, two independent 8-row blocks of the panel in flight per warp.
+        // Block t of the panel holds C rows 8t..8t+7 in the fragment layout of the tile it came from (transposed for
+        // t < k: those come from row tiles), and receives X in the layout of the tile that will read it.
         {
             const double2 wz = lds128(gb + O_W + lane16);     // W[n=lr][2m, 2m+1]
             const double2 wx = lds128(gb + O_WT + lane16);    // W[2m, 2m+1][n=lr]
             const double2 zq = lds128(gb + O_ZR + (lane16 & 48));
-            for (int t0 = warp; t0 < T; t0 += P3_TILES * nwarps) {
-                const unsigned ca = cw + t0 * 512 + lane16, tstep = 512u * nwarps;
-                double2 c[P3_TILES];
-                double z0[P3_TILES], z1[P3_TILES], x0[P3_TILES], x1[P3_TILES], rold[P3_TILES];
+            for (int t0 = warp; t0 < Tpad; t0 += 2 * nwarps) {
+                // no branches in here: a lone warp pays ~30 cycles for every taken one
+                double z0[2], z1[2], x0[2], x1[2], rold[2], dot[2];
+                double2 c[2];
 #pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) c[u] = (t0 + u * nwarps < T) ? lds128(ca + u * tstep) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) rold[u] = (t0 + u * nwarps < T) ? lds64(gb + O_RV + (t0 + u * nwarps) * 64 + lr * 8) : 0.0;
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) { z0[u] = 0.0; z1[u] = 0.0; dmma884(z0[u], z1[u], c[u].x, wz.x); }
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) dmma884(z0[u], z1[u], c[u].y, wz.y);
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) { x0[u] = 0.0; x1[u] = 0.0; dmma884(x0[u], x1[u], z0[u], wx.x); }
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) dmma884(x0[u], x1[u], z1[u], wx.y);
-                double dot[P3_TILES];
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) dot[u] = fma(z1[u], zq.y, z0[u] * zq.x);
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 1);
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 2);
-#pragma unroll
-                for (int u = 0; u < P3_TILES; ++u) {
+                for (int u = 0; u < 2; ++u) {
                     const int t = t0 + u * nwarps;
-                    if (t < T) {
-                        sts128(ca + u * tstep, x0[u], x1[u]);
-                        sts128(ca + u * tstep - (2 + (k & 1)) * pb, z0[u], z1[u]);          // Zb
-                        sts128(ca + u * tstep - (1 + (k & 1)) * pb, -z0[u], -z1[u]);        // Zn
-                        if ((lane & 3) == 0) sts64(gb + O_RV + t * 64 + lr * 8, (t == k) ? dot[u] : rold[u] - dot[u]);   // pivot tile: r_k <- W' zr = D^-1 r_k
-                        if (t == k + 1) {   // look-ahead: the next pivot tile after this step's update, D - Z Z'
-                            double2 d = lds128(gb + O_DN + lane16);
-                            dmma884(d.x, d.y, -z0[u], z0[u]);
-                            dmma884(d.x, d.y, -z1[u], z1[u]);
-                            sts128(gb + O_DB + lane16, d.x, d.y);
-                        }
-                    }
+                    const unsigned blk = cw + t * 512;
+                    const unsigned off0 = (t < k) ? ltr : lane16, off1 = off0 + ((t < k) ? 64u : 8u);
+                    c[u].x = lds64(blk + off0);
+                    c[u].y = lds64(blk + off1);
+                    rold[u] = lds64(gb + O_RV + t * 64 + lr * 8);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {   // pivot block: identity rows, X = D^-1
+                    const bool pv = (t0 + u * nwarps == k);
+                    c[u].x = pv ? ((lr == lc) ? 1.0 : 0.0) : c[u].x;
+                    c[u].y = pv ? ((lr == lc + 1) ? 1.0 : 0.0) : c[u].y;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { z0[u] = 0.0; z1[u] = 0.0; dmma884(z0[u], z1[u], c[u].x, wz.x); }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) dmma884(z0[u], z1[u], c[u].y, wz.y);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { x0[u] = 0.0; x1[u] = 0.0; dmma884(x0[u], x1[u], z0[u], wx.x); }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) dmma884(x0[u], x1[u], z1[u], wx.y);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const unsigned za = gb + ozb + (t0 + u * nwarps) * 512 + lane16;
+                    sts128(za, z0[u], z1[u]);                       // Zb
+                    sts128(za + pb, negd(z0[u]), negd(z1[u]));      // Zn
+                    dot[u] = fma(z1[u], zq.y, z0[u] * zq.x);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 1);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 2);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = t0 + u * nwarps;
+                    const unsigned blk = cw + t * 512;
+                    const unsigned off0 = (t < k) ? ltr : lane16, off1 = off0 + ((t < k) ? 64u : 8u);
+                    const int sg = (t == k) ? (int)0x80000000 : 0;   // pivot tile: -D^-1
+                    sts64(blk + off0, __hiloint2double(__double2hiint(x0[u]) ^ sg, __double2loint(x0[u])));
+                    sts64(blk + off1, __hiloint2double(__double2hiint(x1[u]) ^ sg, __double2loint(x1[u])));
+                    const double rnew = (t == k) ? dot[u] : rold[u] - dot[u];   // r_k <- W' zr = D^-1 r_k
+                    if ((lane & 3) == 0) sts64(gb + O_RV + t * 64 + lr * 8, rnew);
                 }
             }
         }
@@ -393,32 +467,23 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
         group_sync(gid, gthreads);
         PROF_TL(3);
         if (k == 0 && next_group_exists) asm volatile("bar.arrive %0, %1;" ::"r"(8 + gid + 1), "r"(2 * gthreads) : "memory");
-
-        // look-ahead: ONE lane of the warp that finished the next pivot tile factors it (Cholesky of the 8x8 block,
-        // W = L^-1, zr) while the other warps run their trailing update.  Its tile registers are parked in shared
-        // memory meanwhile: the factorisation needs the registers of a whole thread.
-        if (k + 1 < T && warp == pw) {
-#pragma unroll
-            for (int s = 0; s < REG_SLOTS; ++s) sts128(gb + O_PARK + s * 512 + lane16, acc[s][0], acc[s][1]);
-            if (lane == 0) pivot_tile(gb, k + 1);
-#pragma unroll
-            for (int s = 0; s < REG_SLOTS; ++s) { const double2 v = lds128(gb + O_PARK + s * 512 + lane16); acc[s][0] = v.x; acc[s][1] = v.y; }
-        }
-        pw = (pw + 1 == nwarps) ? 0 : pw + 1;
+        write_descriptors(dw + lane * 8, mytile, k, cw, cn, gb);   // read back after the update (same warp: __syncwarp)
         PROF_TL(4);
-        // bulk: A_ij -= Z_i Z_j' on every tile of the warp (tiles of row / column k are overwritten right after);
-        // operands are fetched one tile ahead (a warp issues in order: LDS and SHFL latencies must be covered by hand)
+        // bulk: A_ij -= Z_i Z_j' on every tile of the warp (tiles of row / column k are overwritten right after).
+        // Operand addresses come from the warp's table; everything is fetched one tile ahead (a warp issues in order).
         {
             const unsigned zbb = gb + ozb + lane16, znb = zbb + pb;
-            unsigned o0 = __shfl_sync(0xffffffffu, myoffs, 0);
-            double2 a_0 = lds128(znb + (o0 & 0xffffu)), b_0 = lds128(zbb + (o0 >> 16));
+            uint2 o = lds64u(tw);
+            double2 a_0 = lds128(znb + o.x), b_0 = lds128(zbb + o.y);
+            uint2 o1 = lds64u(tw + 8);
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
                 double2 a_1 = a_0, b_1 = b_0;
+                uint2 o2 = o1;
                 if (s + 1 < SLOTS) {
-                    const unsigned o1 = __shfl_sync(0xffffffffu, myoffs, s + 1);
-                    a_1 = lds128(znb + (o1 & 0xffffu));
-                    b_1 = lds128(zbb + (o1 >> 16));
+                    if ((amask >> (s + 1)) & 1u) a_1 = lds128(znb + o1.x);
+                    b_1 = lds128(zbb + o1.y);
+                    if (s + 2 < SLOTS) o2 = lds64u(tw + (s + 2) * 8);
                 }
                 if (s < REG_SLOTS) {
                     dmma884(acc[s < REG_SLOTS ? s : 0][0], acc[s < REG_SLOTS ? s : 0][1], a_0.x, b_0.x);
@@ -429,17 +494,18 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
                     dmma884(d.x, d.y, a_0.y, b_0.y);
                     sts128(tm + (s - REG_SLOTS) * 512, d.x, d.y);
                 }
-                a_0 = a_1; b_0 = b_1;
+                a_0 = a_1; b_0 = b_1; o1 = o2;
             }
         }
         PROF_TL(5);
         // scan: final values of row / column k, next panel, raw pivot tile k+2
-        scan_tiles(acc, tm, mytile, k, lane16, lanet, cw, cn, gb, false);
+        __syncwarp();
+        scan_tiles(acc, tm, dw, lane16);
         PROF_TL(6);
     }
     group_sync(gid, gthreads);
 #ifdef GPCC_FRAG_PROF
-    if (blockIdx.x == 0) for (int i = tid; i < T * 8 * 12; i += gthreads) if ((i % 12) / nwarps == gid) g_frag_tl[i] = tlbuf[i];
+    if (blockIdx.x == 0) for (int i = tid; i < T * 8 * 16; i += gthreads) if ((i % 16) / (nwarps + 1) == gid) g_frag_tl[i] = tlbuf[i];
 #endif
 
     // ---- log-determinant, info, quadratic form -------------------------------------------------------------------
@@ -471,13 +537,15 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
 
     // ---- gradient: W = a a' - K~^-1 contracted with K and dK/drho, eight tiles at a time through the staging buffer -
     double es = 0.0;
+    if (!helper)
 #pragma unroll
     for (int c = 0; c < SLOTS / 8; ++c) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) { double g0, g1; TILE_GET(c * 8 + u, g0, g1); st[u * 32 + lane] = make_double2(g0, g1); }
         __syncwarp();
         for (int u = 0; u < 8; ++u) {
-            const int q = (c * 8 + u) * nwarps + warp;
+            const int sl = c * 8 + u;
+            const int q = ((sl / CHUNK) * nwarps + warp) * CHUNK + sl % CHUNK;
             if (q < ntiles) {
                 int ti, tj;
                 tile_of(q, ti, tj);
@@ -529,7 +597,7 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
         srow[i] = s;
     }
     group_sync(gid, gthreads);
-    for (int pb = warp; pb < L; pb += nwarps) {
+    for (int pb = warp; pb < L; pb += nwarps + 1) {
         double s = 0.0;
         for (int i = p.band_start[pb] + lane; i < p.band_start[pb + 1]; i += 32) s += srow[i];
         s = warp_sum(s);
@@ -538,11 +606,14 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int nmat, int 
     if (tid == 0) b.grad[(size_t)e * (L + 1) + L] = es;   // 0.5 * sum_full = sum over the strict lower triangle
 }
 
+int padded_T(int T, int nwarps) { return (T + 2 * nwarps - 1) / (2 * nwarps) * (2 * nwarps); }
+
 size_t group_smem_doubles(int T, int nwarps, int want_grad) {
-    const int Np = 8 * T;
-    const size_t panel = (size_t)4 * T * 64, stage = (size_t)nwarps * 512;
-    size_t doubles = (O_TM + (size_t)nwarps * (SLOTS - REG_SLOTS) * 512) / 8 + (panel > stage ? panel : stage) + (size_t)Np * 4 +
-                     (want_grad ? (size_t)T * T * 8 + (size_t)T * 8 : 0) + (size_t)(Np + 1) / 2 + 2;
+    const int Np = 8 * T, Tpad = padded_T(T, nwarps);
+    const size_t panel = (size_t)4 * Tpad * 64, stage = (size_t)nwarps * 512;
+    const size_t part = want_grad ? (size_t)T * T * 8 + (size_t)T * 8 : 0;
+    size_t doubles = (O_TM + (size_t)nwarps * ((SLOTS - REG_SLOTS) * 512 + 512)) / 8 + (panel > stage ? panel : stage) + (size_t)Np * 4 +
+                     (stage + part <= panel ? 0 : part) + (size_t)(Np + 1) / 2 + 2;
     return (doubles + 1) & ~(size_t)1;   // keep every group 16-byte aligned
 }
 
@@ -550,22 +621,31 @@ template <int KID>
 cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStream_t s) {
     const int ntiles = T * (T + 1) / 2;
     const int nwarps = (ntiles + SLOTS - 1) / SLOTS;
-    const int gthreads = nwarps * 32;
+    const int gthreads = (nwarps + 1) * 32;   // + the helper warp
     static const int nmat_cap = getenv("GPCC_FRAG_NMAT") ? atoi(getenv("GPCC_FRAG_NMAT")) : 4;
-    int nmat = MAX_THREADS / gthreads;
-    if (nmat > nmat_cap) nmat = nmat_cap;
-    if (nmat < 1) nmat = 1;
     const size_t gd = group_smem_doubles(T, nwarps, b.want_grad);
+    const int hwpg = 4 * ((nwarps + 2) / 3);   // hardware warps per matrix: three tile warps per quad + the helper / spare slot
+    int nmat = (MAX_THREADS / 32) / hwpg;
+    if (nmat > nmat_cap) nmat = nmat_cap;
+    while (nmat > 1 && gd * 8 * nmat > 220 * 1024) --nmat;
+    if (nmat < 1) nmat = 1;
     auto kfn = small_frag_kernel<KID>;
     size_t extra = 0;
 #ifdef GPCC_FRAG_PROF
-    extra = 32 * 8 * 12 * 8;
+    extra = (size_t)T * 8 * 16 * 8;
 #endif
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
     const int blocks = (b.M + nmat - 1) / nmat;
-    kfn<<<blocks, gthreads * nmat, gd * 8 * nmat + extra, s>>>(p, b, T, gthreads, nmat, (int)gd);
-    return cudaGetLastError();
+    kfn<<<blocks, hwpg * 32 * nmat, gd * 8 * nmat + extra, s>>>(p, b, T, padded_T(T, nwarps), gthreads, hwpg, nmat, (int)gd);
+    cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kfn);
+        fprintf(stderr, "[small_frag] launch failed: %s; threads %d, dynamic smem %zu B, kernel: %d regs, %zu B static smem, max %d threads/block, max dynamic smem %d\n",
+                cudaGetErrorString(rc), hwpg * 32 * nmat, gd * 8 * nmat + extra, fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
+    }
+    return rc;
 }
 
 }  // namespace
@@ -577,28 +657,28 @@ cudaError_t small_frag_launch(const DevProblem& p, const EvalBatch& b, cudaStrea
 #ifdef GPCC_FRAG_PROF
     cudaError_t rc = launch_kid<K_M32>(p, b, T, s);
     cudaStreamSynchronize(s);
-    static long long tl[32 * 8 * 12];
+    static long long tl[32 * 8 * 16];
     cudaMemcpyFromSymbol(tl, g_frag_tl, sizeof(tl));
     const int nw = ((T * (T + 1) / 2 + 31) / 32);
-    for (int g = 0; g < 12 / nw && g < 4; ++g) {
+    for (int g = 0; g < 14 / (nw + 1) && g < 4; ++g) {
         // slots: 0 step start, 1 after B1, 2 P3 done, 3 after B2, 4 look-ahead pivot done, 5 bulk done, 6 scan done
         double acc[6] = {0}; long long first = 0, last = 0;
         for (int k = 1; k < T; ++k) {
             long long mn0 = 1LL << 62, mx[8] = {0};
-            for (int w = 0; w < nw; ++w) {
-                const long long* q = tl + (k * 8) * 12 + w + nw * g;
+            for (int w = 0; w <= nw; ++w) {
+                const long long* q = tl + (k * 8) * 16 + w + (nw + 1) * g;
                 mn0 = q[0] < mn0 ? q[0] : mn0;
-                for (int sl = 0; sl < 7; ++sl) mx[sl] = q[12 * sl] > mx[sl] ? q[12 * sl] : mx[sl];
+                for (int sl = 0; sl < 7; ++sl) mx[sl] = q[16 * sl] > mx[sl] ? q[16 * sl] : mx[sl];
             }
             if (k == 1) first = mn0;
             last = mx[6];
             acc[0] += mx[1] - mn0; acc[1] += mx[3] - mx[1]; acc[2] += mx[4] - mx[3]; acc[3] += mx[5] - mx[4]; acc[4] += mx[6] - mx[5];
         }
         if (last == 0) continue;
-        if (g == 0) for (int w = 0; w < nw; ++w) {
-            const long long* q = tl + (5 * 8) * 12 + w;
+        if (g == 0) for (int w = 0; w <= nw; ++w) {
+            const long long* q = tl + (5 * 8) * 16 + w;
             fprintf(stderr, "[frag tl] T=%d k=5 warp %d: start %lld | after B1 %lld | P3 done %lld | after B2 %lld | pivot done %lld | bulk done %lld | scan done %lld\n", T, w,
-                    q[0] - tl[5 * 8 * 12], q[12] - tl[5 * 8 * 12], q[24] - tl[5 * 8 * 12], q[36] - tl[5 * 8 * 12], q[48] - tl[5 * 8 * 12], q[60] - tl[5 * 8 * 12], q[72] - tl[5 * 8 * 12]);
+                    q[0] - tl[5 * 8 * 16], q[16] - tl[5 * 8 * 16], q[32] - tl[5 * 8 * 16], q[48] - tl[5 * 8 * 16], q[64] - tl[5 * 8 * 16], q[80] - tl[5 * 8 * 16], q[96] - tl[5 * 8 * 16]);
         }
         fprintf(stderr, "[frag tl] T=%d group %d per step (slowest warp): B1 %.0f | P3+B2 %.0f | pivot %.0f | bulk %.0f | scan %.0f | step %.0f\n", T, g,
                 acc[0] / (T - 1), acc[1] / (T - 1), acc[2] / (T - 1), acc[3] / (T - 1), acc[4] / (T - 1), (double)(last - first) / (T - 1));
