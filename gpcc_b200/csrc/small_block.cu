@@ -206,7 +206,7 @@ small_block_kernel(DevProblem p, EvalBatch b, int T, int gthreads, int smem_doub
             bandv[i] = -1 - i;
         }
     }
-    if (tid < 128) Wb[tid] = 0.0;
+    for (int i = tid; i < 128; i += gthreads) Wb[i] = 0.0;
     if (tid == 0) misc[0] = 0.0;
     group_sync(gid, gthreads);
 

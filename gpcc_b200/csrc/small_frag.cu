@@ -63,7 +63,7 @@ constexpr int REG_SLOTS = 20;   // ... of which this many live in registers (80 
                                 // With all 32 in registers ptxas keeps some of them in LOCAL memory instead, which is worse.
 constexpr int CHUNK = 4;        // consecutive tiles (row major over the lower triangle) dealt to a warp at a time: the
                                 // A operand of the update is reloaded only when the tile row changes
-constexpr unsigned O_W = 0, O_WT = 512, O_ZR = 1024, O_MISC = 1088, O_RED = 1152, O_DB = 1280, O_DN = 1792, O_RV = 2304;
+constexpr unsigned O_W = 0, O_WT = 512, O_ZR = 1024, O_MISC = 1088, O_RED = 1152, O_DB = 1280, O_DN = 1792, O_RV = 2816;   // Dn: two buffers
 constexpr unsigned O_PIV = O_RV + 3072, O_TM = O_PIV + 2048;
 // from O_TM on (sizes depend on the launch): [nwarps][4] memory-resident tiles, [nwarps][32] scan descriptors (8 B),
 // [nwarps][32] update-operand offsets (8 B), then Zb, Zn, Cb[0], Cb[1] (pb = 512 Tpad bytes each)
@@ -210,7 +210,7 @@ __device__ __forceinline__ void write_descriptors(unsigned da, int mytile, int k
         if (mtj == kw) src = cw + mti * 512; else if (mti == kw) src = cw + mtj * 512;
         if (mtj == kn) { if (mti != kn) dst = cn + mti * 512; else if (kw < 0) dst = gb + O_DB; }
         else if (mti == kn) dst = cn + mtj * 512;
-        else if (mti == kp && mtj == kp) dst = gb + O_DN;
+        else if (mti == kp && mtj == kp) dst = gb + O_DN + (kw & 1) * 512;   // read by the helper during step kw+1, while the scan of that step fills the other buffer
     }
     sts64u(da, src, dst);
 }
@@ -316,7 +316,7 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
         rv[i] = r;
         if (i < Np) { tsh[i] = ts; av[i] = al; sbv[i] = sb; dadd[i] = dd; bandv[i] = bi; }
     }
-    if (tid < 128) Wb[tid] = 0.0;
+    for (int i = tid; i < 128; i += gthreads) Wb[i] = 0.0;
     if (tid == 0) misc[0] = 0.0;
     // Slot s of this warp is tile q = ((s / CHUNK) * nwarps + warp) * CHUNK + s % CHUNK (chunks of consecutive tiles dealt
     // round robin); lane s keeps that tile's coordinates for the whole warp and writes its entry of the warp's
@@ -390,7 +390,7 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
             if (k == 0 && next_group_exists) asm volatile("bar.arrive %0, %1;" ::"r"(8 + gid + 1), "r"(2 * gthreads) : "memory");
             if (k + 1 < T) {
                 const double2 z = lds128(gb + ozb + (k + 1) * 512 + lane16);
-                double2 d = lds128(gb + O_DN + lane16);
+                double2 d = lds128(gb + O_DN + ((k + 1) & 1) * 512 + lane16);
                 dmma884(d.x, d.y, negd(z.x), z.x);
                 dmma884(d.x, d.y, negd(z.y), z.y);
                 sts128(gb + O_DB + lane16, d.x, d.y);

@@ -31,6 +31,11 @@ namespace gpcc {
 namespace {
 
 constexpr int TS = SMALL_TILE;  // 8
+
+// Two matrices may share one CTA (NMAT = 2): each "group" of threads owns one matrix, its own slice of shared memory and
+// its own named barrier.  With 6 warps per matrix, warps 0-5 and 6-11 of one CTA land on the four schedulers 3 + 3 + 3 + 3;
+// two separate CTAs of 6 warps land 4 + 4 + 2 + 2, i.e. two schedulers carry twice the DFMA load of the others.
+#define GROUP_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(nthreads) : "memory")
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
 // Chunked layout of the per-point vectors in shared memory: [pair-of-rows part (4)][tile (<=32)][2], with a
@@ -82,7 +87,7 @@ __device__ __forceinline__ void publish(const double (&A)[8][8], int ti, int tj,
 
 template <int KK>
 __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, int tk, int k, int N, int T, int Np,
-                                           double* cbuf, double* pbuf, double* piv, bool active) {
+                                           double* cbuf, double* pbuf, double* piv, bool active, int gid, int nthreads) {
     const double* cb = cbuf + (k & 1) * VLEN;
     double v[8];
     load8(cb, tj, T, v);
@@ -116,7 +121,7 @@ __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, in
         if (KK < 7) publish<(KK + 1) & 7>(A, ti, tj, tk, kn, T, nb, pbuf + (kn & 1), piv, active);
         else        publish<0>(A, ti, tj, tk + 1, kn, T, nb, pbuf + (kn & 1), piv, active);
     }
-    __syncthreads();
+    GROUP_SYNC();
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -126,25 +131,29 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Deterministic block sum: xor-tree inside each warp, then thread 0 adds the warp totals in order.
-__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nthreads) {
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nthreads, int gid) {
     v = warp_sum(v);
-    __syncthreads();
+    GROUP_SYNC();
     if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
+    GROUP_SYNC();
     double s = 0.0;
     const int nw = (nthreads + 31) >> 5;
     for (int w = 0; w < nw; ++w) s += red[w];
     return s;
 }
 
-template <int KID, int MAXTHREADS, int MINBLOCKS>
+template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
-small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
-    extern __shared__ __align__(16) double smem[];
+small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
+    extern __shared__ __align__(16) double smem_all[];
     const int N = p.N, L = p.L;
     const int Np = T * TS;
-    const int e = blockIdx.x;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int nthreads = blockDim.x / NMAT;
+    const int gid = (NMAT == 1) ? 0 : (int)threadIdx.x / nthreads;
+    const int tid = (int)threadIdx.x - gid * nthreads;
+    const int e = blockIdx.x * NMAT + gid;
+    if (e >= b.M) return;   // a whole group without work: its named barrier is never used
+    double* smem = smem_all + (size_t)gid * group_doubles;
     const int ntiles = T * (T + 1) / 2;
     const bool active = tid < ntiles;
     const int q = active ? tid : ntiles - 1;
@@ -162,6 +171,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
     double* abuf = piv + VLEN;      // residual r, later a = K~^-1 r            (chunk layout)
     double* pbuf = abuf + VLEN;     // 2 pivot reciprocals (+2 pad)
     double* red = pbuf + 4;         // 64 reduction slots
+    int* s_bad_p = reinterpret_cast<int*>(red + 48);
     double* part = red + 64;        // [T][T][8] gradient row-sum partials (gradient only)
     int* bandv = reinterpret_cast<int*>(part + (b.want_grad ? T * T * 8 : 0));  // [Np] natural
 
@@ -183,7 +193,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
             bandv[i] = -1 - i;
         }
     }
-    __syncthreads();
+    GROUP_SYNC();
 
     // ---- assembly of the bordered matrix tile in registers --------------------------------------
     double A[8][8];
@@ -214,22 +224,22 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
             }
         }
     }
-    __syncthreads();   // everyone has read abuf/tsh before cbuf traffic starts (abuf is reused later)
+    GROUP_SYNC();   // everyone has read abuf/tsh before cbuf traffic starts (abuf is reused later)
 
     // ---- publish column 0, then N sweep steps ----------------------------------------------------
     publish<0>(A, ti, tj, 0, 0, T, cbuf, pbuf, piv, active);
-    __syncthreads();
+    GROUP_SYNC();
     for (int tk = 0; tk < T; ++tk) {
         const int k0 = tk * 8;
         if (k0 >= N) break;
-        sweep_step<0>(A, ti, tj, tk, k0 + 0, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 1 >= N) break;
-        sweep_step<1>(A, ti, tj, tk, k0 + 1, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 2 >= N) break;
-        sweep_step<2>(A, ti, tj, tk, k0 + 2, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 3 >= N) break;
-        sweep_step<3>(A, ti, tj, tk, k0 + 3, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 4 >= N) break;
-        sweep_step<4>(A, ti, tj, tk, k0 + 4, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 5 >= N) break;
-        sweep_step<5>(A, ti, tj, tk, k0 + 5, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 6 >= N) break;
-        sweep_step<6>(A, ti, tj, tk, k0 + 6, N, T, Np, cbuf, pbuf, piv, active); if (k0 + 7 >= N) break;
-        sweep_step<7>(A, ti, tj, tk, k0 + 7, N, T, Np, cbuf, pbuf, piv, active);
+        sweep_step<0>(A, ti, tj, tk, k0 + 0, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 1 >= N) break;
+        sweep_step<1>(A, ti, tj, tk, k0 + 1, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 2 >= N) break;
+        sweep_step<2>(A, ti, tj, tk, k0 + 2, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 3 >= N) break;
+        sweep_step<3>(A, ti, tj, tk, k0 + 3, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 4 >= N) break;
+        sweep_step<4>(A, ti, tj, tk, k0 + 4, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 5 >= N) break;
+        sweep_step<5>(A, ti, tj, tk, k0 + 5, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 6 >= N) break;
+        sweep_step<6>(A, ti, tj, tk, k0 + 6, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 7 >= N) break;
+        sweep_step<7>(A, ti, tj, tk, k0 + 7, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads);
     }
 
     // ---- log-determinant, info, quadratic form ---------------------------------------------------
@@ -240,13 +250,12 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
         const double d = piv[k];
         if (!(d > 0.0)) bad = min(bad, k + 1); else ld += log(d);
     }
-    ld = block_sum(ld, red, tid, nthreads);
-    __shared__ int s_bad;
-    if (tid == 0) s_bad = INT_MAX;
-    __syncthreads();
-    if (bad != INT_MAX) atomicMin(&s_bad, bad);   // min is order independent: deterministic
-    __syncthreads();
-    const int info = (s_bad == INT_MAX) ? 0 : s_bad;
+    ld = block_sum(ld, red, tid, nthreads, gid);
+    if (tid == 0) *s_bad_p = INT_MAX;
+    GROUP_SYNC();
+    if (bad != INT_MAX) atomicMin(s_bad_p, bad);   // min is order independent: deterministic
+    GROUP_SYNC();
+    const int info = (*s_bad_p == INT_MAX) ? 0 : *s_bad_p;
 
     if (active && ti == tN && tj == tN) {
         double qv = 0.0;
@@ -254,7 +263,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
         for (int r = 0; r < 8; ++r) if (r == rN) qv = -A[r][r];
         red[32] = qv;
     }
-    __syncthreads();
+    GROUP_SYNC();
     const double quad = red[32];
     const double ll = -0.5 * ((double)N * LOG2PI + ld + quad);   // logpdf(MvNormal(bbar,K), Y)  (:139)
     if (tid == 0) {
@@ -279,7 +288,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
         }
         store8(abuf, tj, T, vals);
     }
-    __syncthreads();
+    GROUP_SYNC();
 
     if (b.dump_kinv && active) {   // K~^-1 = -(swept matrix); written once per gpcc call (postb / pred), not in the fit loop
         double* out = b.dump_kinv + (size_t)e * N * N;
@@ -346,7 +355,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) part[(ti * T + tj) * 8 + r] = rows[r];
     }
-    es = block_sum(active ? es : 0.0, red, tid, nthreads);   // (contains the __syncthreads that orders `part`)
+    es = block_sum(active ? es : 0.0, red, tid, nthreads, gid);   // (contains the __syncthreads that orders `part`)
 
     // s_i = sum_j W_ij K_ij (full row);  dlogL/dalpha_p = (1/alpha_p) sum_{i in band p} s_i
     double* srow = cbuf;   // natural layout, reuse
@@ -356,7 +365,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T) {
         for (int src = 0; src < T; ++src) s += pp[src * 8];
         srow[i] = s;
     }
-    __syncthreads();
+    GROUP_SYNC();
     const int warp = tid >> 5, lane = tid & 31, nwarps = (nthreads + 31) >> 5;
     for (int pb = warp; pb < L; pb += nwarps) {
         double s = 0.0;
@@ -379,28 +388,37 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
     const int threads = (ntiles + 31) / 32 * 32;
     const size_t sm = smem_bytes(T, b.want_grad);
     static const int variant = getenv("GPCC_SMALL_VARIANT") ? atoi(getenv("GPCC_SMALL_VARIANT")) : 1;
+    const int gd = (int)((sm + 15) / 16 * 2);   // doubles per group, 16-byte aligned
     if (threads <= 128) {
-        if (variant == 2) {
-            auto kfn = small_sweep_kernel<KID, 128, 3>;
+        if (variant == 3) {   // three matrices per CTA: 12 warps, 3 per scheduler
+            auto kfn = small_sweep_kernel<KID, 384, 1, 3>;
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * (int)((smem_bytes(15, 1) + 15) / 16 * 2));
+            kfn<<<(b.M + 2) / 3, 3 * threads, (size_t)3 * gd * 8, s>>>(p, b, T, gd);
+        } else if (variant == 2) {
+            auto kfn = small_sweep_kernel<KID, 128, 3, 1>;
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
-            kfn<<<b.M, threads, sm, s>>>(p, b, T);
+            kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
         } else {
-            auto kfn = small_sweep_kernel<KID, 128, 2>;
+            auto kfn = small_sweep_kernel<KID, 128, 2, 1>;
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
-            kfn<<<b.M, threads, sm, s>>>(p, b, T);
+            kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
         }
+    } else if (threads <= 192 && variant == 3) {   // two matrices per CTA: 12 warps, 3 per scheduler
+        auto kfn = small_sweep_kernel<KID, 384, 1, 2>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (int)((smem_bytes(19, 1) + 15) / 16 * 2));
+        kfn<<<(b.M + 1) / 2, 2 * threads, (size_t)2 * gd * 8, s>>>(p, b, T, gd);
     } else if (threads <= 192 && variant == 1) {
-        auto kfn = small_sweep_kernel<KID, 192, 2>;
+        auto kfn = small_sweep_kernel<KID, 192, 2, 1>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T);
+        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
     } else if (threads <= 224) {
-        auto kfn = small_sweep_kernel<KID, 224, 1>;
+        auto kfn = small_sweep_kernel<KID, 224, 1, 1>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(20, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T);
+        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
     } else {
-        auto kfn = small_sweep_kernel<KID, 352, 1>;
+        auto kfn = small_sweep_kernel<KID, 352, 1, 1>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(SMALL_MAX_T, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T);
+        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
     }
     return cudaGetLastError();
 }

@@ -348,9 +348,18 @@ def test_prior_with_minus_infinity_and_iteration_cap_zero(ctx):
     assert np.allclose(r0["loglikel"], scr, rtol=1e-14) and np.all(r0["info"] == 1) and np.all(r0["nfev"] == 5)
 
 
-def test_experimental_dmma_fused_kernel_agrees(ctx):
-    """small_dmma.cu (rank-8 block sweep on DMMA for the register-resident sizes) is off by default because it is slower
-    than the DFMA sweep below N~200 (profiles/README.md); it must still be exact.  The switch is read once per process."""
+@pytest.mark.parametrize("switch", [
+    {"GPCC_SMALL_DMMA": "1"},                                  # small_dmma.cu: rank-8 block sweep, DMMA update, tiles per warp
+    {"GPCC_SMALL_BLOCK": "1"},                                 # small_block.cu: blocked DFMA sweep, one matrix per CTA
+    {"GPCC_SMALL_BLOCK": "1", "GPCC_BLOCK_VARIANT": "1"},      #                 two matrices per CTA (named barriers)
+    {"GPCC_SMALL_FRAG": "1"},                                  # small_frag.cu: fragment layout, DMMA panel + update, helper warp
+    {"GPCC_SMALL_FRAG": "1", "GPCC_FRAG_NMAT": "1"},
+    {"GPCC_SMALL_VARIANT": "3"},                               # small_sweep.cu with several matrices per CTA
+], ids=lambda d: "+".join(f"{k[5:]}={v}" for k, v in d.items()))
+def test_experimental_fused_kernels_agree(ctx, switch):
+    """The alternative small-N evaluators are off by default because none of them beats the rank-1 DFMA sweep yet
+    (profiles/README.md); they must still be exact: golden log-likelihoods and gradients, LAPACK-style info on a matrix
+    that is not positive definite, ragged / tiny sizes against the oracle.  The switches are read once per process."""
     import os, subprocess, sys
     code = (
         "import numpy as np, sys; sys.path.insert(0, %r)\n"
@@ -363,8 +372,35 @@ def test_experimental_dmma_fused_kernel_agrees(ctx):
         "    assert np.all(info == 0)\n"
         "    assert np.max(np.abs(ll - g['loglik']) / np.abs(g['loglik'])) < 1e-10, name\n"
         "    assert np.max(np.abs(grad - g['grad']) / np.max(np.abs(g['grad']), axis=1, keepdims=True)) < 1e-8, name\n"
-        "print('DMMA-OK')\n"
+        "    ll2, info2 = p.loglik_batch(g['delays'][:3], g['alpha'][:3], g['rho'][:3])\n"
+        "    assert np.array_equal(ll2, ll[:3]), name\n"
+        "for nper, kernel in (([25], 'matern32'), ([9, 8, 7, 6, 9, 8, 7, 6], 'OU'), ([3, 2], 'rbf'), ([70, 60, 61], 'matern52')):\n"
+        "    t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=11, span=15.0)\n"
+        "    L = len(nper); op = oracle.Problem(t, y, s, kernel); p = gpcc_b200.Problem(t, y, s, kernel)\n"
+        "    rg = np.random.default_rng(4); M = 7\n"
+        "    delays = np.zeros((M, L)); delays[:, 1:] = rg.uniform(-3, 6, (M, L - 1))\n"
+        "    alpha, rho = rg.uniform(0.5, 2.0, (M, L)), rg.uniform(0.5, 6.0, M)\n"
+        "    ll, grad, info = p.loglik_batch(delays, alpha, rho, want_grad=True)\n"
+        "    for m in range(M):\n"
+        "        rl, rgd = op.loglik_grad(delays[m], alpha[m], rho[m])\n"
+        "        assert abs(ll[m] - rl) / abs(rl) < 1e-10 and np.max(np.abs(grad[m] - rgd)) / np.max(np.abs(rgd)) < 1e-8, (nper, m)\n"
+        "t = [np.array([1.0, 1.0, 2.0, 3.0]), np.array([1.5, 2.5, 2.5])]; y = [np.array([1.0, 2.0, 1.5, 0.5]), np.array([3.0, 2.0, 2.5])]\n"
+        "p = gpcc_b200.Problem(t, y, [np.zeros(4), np.zeros(3)], 'rbf')      # duplicated times, zero noise: singular\n"
+        "ll, grad, info = p.loglik_batch([[0.0, 0.0]], [[1.0, 1.0]], [1.0], want_grad=True)\n"
+        "assert info[0] > 0 and ll[0] == -np.inf and np.all(grad == 0.0), (ll, info)\n"
+        "g = load_golden('fit_cfg1_cfg2')\n"
+        "loglikel, pred, (alpha, postb, rho) = gpcc_b200.gpcc(g['tb'], g['yb'], g['sb'], kernel=gpcc_b200.matern32, delays=g['truedelays'],\n"
+        "                                                    iterations=1000, rhomax=300, theta0=g['theta0'])\n"
+        "assert abs(loglikel - float(g['loglikel'])) < 1e-6\n"
+        "p = gpcc_b200.Problem(g['tb'], g['yb'], g['sb'], 'matern32')\n"
+        "mu, S = p.postb(g['truedelays'], g['alpha'], float(g['rho']))\n"
+        "assert np.allclose(mu, g['postb_mu'], rtol=1e-8) and np.allclose(S, g['postb_Sigma'], rtol=1e-8)\n"
+        "m_, sd_, _, _ = p.predict(g['truedelays'], g['alpha'], float(g['rho']), [g['ttest']] * 2)\n"
+        "nt = len(g['ttest'])\n"
+        "assert np.max(np.abs(m_.reshape(2, nt) - g['pred_mu']) / np.abs(g['pred_mu'])) < 1e-8\n"
+        "assert np.max(np.abs(sd_.reshape(2, nt) - g['pred_sd']) / g['pred_sd']) < 1e-8\n"
+        "print('VARIANT-OK')\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GPCC_SMALL_DMMA="1", PYTHONPATH=os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "DMMA-OK" in r.stdout, r.stderr[-2000:]
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.abspath(__file__)), **switch)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "VARIANT-OK" in r.stdout, (r.stdout[-500:], r.stderr[-2500:])
