@@ -176,6 +176,8 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
     EvalSlot& q0 = s.slot[0];
     LbfgsOptions lo;
     lo.max_iter = o.max_iter; lo.gtol = o.gtol; lo.ftol = o.ftol; lo.history = o.history;
+    static const double dec_env = getenv("GPCC_LBFGS_DEC") ? atof(getenv("GPCC_LBFGS_DEC")) : 0.0;   // experiment switch
+    lo.dec_tol = dec_env;
 
     std::vector<LbfgsState> st(m);
     // ---- stage 1: screening of the P start points (:207-209), batched over all candidates -----------

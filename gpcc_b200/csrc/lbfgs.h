@@ -20,6 +20,7 @@ struct LbfgsOptions {
     double ftol = 1e-13;
     int history = 8;
     int max_ls = 30;
+    double dec_tol = 0.0;   // > 0: stop when the quasi-Newton estimate of the remaining decrease, 0.5 g'Hg, is below it
 };
 
 struct LbfgsState {
@@ -128,6 +129,10 @@ struct LbfgsState {
         else small_df = 0;
         if (iters >= o.max_iter) { status = ITER_CAP; return; }
         new_direction(false);
+        // Newton decrement: with a full set of curvature pairs (history >= n) the two-loop recursion applies a good
+        // inverse-Hessian estimate, and -g'd/2 = g'Hg/2 predicts f - f* .  Stopping there instead of at gtol / ftol saves
+        // the last few iterations of every candidate, which only polish digits 8-13 of an optimum needed to 1e-6.
+        if (o.dec_tol > 0.0 && hcount >= n && -0.5 * gd0 <= o.dec_tol) status = CONVERGED;
     }
 
     // Feed the evaluation at xt (ok=false: matrix not PD / non-finite).  Afterwards either status != RUNNING

@@ -124,6 +124,98 @@ __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, in
     GROUP_SYNC();
 }
 
+// ---- branch-free form of the step (BF = true) -------------------------------------------------------------------------
+// Measured on B200 (profiles/README.md, round-1 session 2): a warp issues in order and a lone warp pays ~25-30 cycles for
+// every taken branch and ~30 for every shared-memory round trip, so with two or three warps per scheduler the eight
+// branches of the step above (loop exits, the vote around `publish`, its divergent owner paths) are a fifth of the
+// step.  Here the step is straight-line code: predicated stores for the owners (inline PTX, so that they cannot turn
+// back into branches), a Newton reciprocal under the same predicate instead of the IEEE division, 32-bit shared-window
+// addresses (one register per pointer instead of two: fewer spills at 168 registers), and no exit tests inside full tiles.
+__device__ __forceinline__ double2 lds_v2(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_pred(unsigned a, double v, int flag) {
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p st.shared.f64 [%0], %1; }" ::"r"(a), "d"(v), "r"(flag) : "memory");
+}
+// pivot d of the next step -> piv[kn], 1/d -> pslot, only where flag is set (the thread that owns the diagonal element)
+__device__ __forceinline__ void publish_pivot(unsigned piv_a, unsigned pslot_a, double d, int flag) {
+    asm volatile(
+        "{ .reg .pred p; .reg .f64 x, e, n;\n"
+        "  setp.ne.s32 p, %3, 0;\n"
+        "  @p rcp.approx.ftz.f64 x, %2;\n"
+        "  @p neg.f64 n, %2;\n"
+        "  @p fma.rn.f64 e, n, x, 0d3FF0000000000000;\n"
+        "  @p fma.rn.f64 x, x, e, x;\n"
+        "  @p fma.rn.f64 e, n, x, 0d3FF0000000000000;\n"
+        "  @p fma.rn.f64 x, x, e, x;\n"
+        "  @p fma.rn.f64 e, n, x, 0d3FF0000000000000;\n"
+        "  @p fma.rn.f64 x, x, e, x;\n"
+        "  @p st.shared.f64 [%0], %2;\n"
+        "  @p st.shared.f64 [%1], x;\n"
+        "}" ::"r"(piv_a), "r"(pslot_a), "d"(d), "r"(flag) : "memory");
+}
+// a_ti / a_tj: shared address of this thread's row / column pair slot in broadcast buffer 0 (cbuf + 2 ti, cbuf + 2 tj);
+// buffers alternate with the step parity, VLEN doubles apart; parts (row pairs) are CS doubles apart.
+template <int KKN>
+__device__ __forceinline__ void publish_bf(const double (&A)[8][8], int pc, int prw, unsigned dst_ti, unsigned dst_tj,
+                                           unsigned piv_a, unsigned pslot_a) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {   // column kn from its tile column; on the diagonal tile the part above the diagonal comes from the row
+        const double val = (r < KKN) ? (prw ? A[KKN][r] : A[r][KKN]) : A[r][KKN];
+        sts_pred(dst_ti + ((r >> 1) * CS + (r & 1)) * 8, val, pc);
+    }
+    const int ronly = prw & (pc ^ 1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sts_pred(dst_tj + ((c >> 1) * CS + (c & 1)) * 8, A[KKN][c], ronly);
+    publish_pivot(piv_a, pslot_a, A[KKN][KKN], pc & prw);
+}
+template <int KK, bool LAST>
+__device__ __forceinline__ void sweep_step_bf(double (&A)[8][8], int ti, int tj, int tk, int k, unsigned a_ti, unsigned a_tj,
+                                              unsigned pbuf_a, unsigned piv_a, int active, int gid, int nthreads) {
+    constexpr unsigned BUF = (KK & 1) * VLEN * 8, NBUF = ((KK + 1) & 1) * VLEN * 8;
+    double v[8];
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+        const double2 t = lds_v2(a_tj + BUF + part * CS * 8);
+        v[2 * part] = t.x;
+        v[2 * part + 1] = t.y;
+    }
+    const double pr = lds_f64(pbuf_a + (KK & 1) * 8);
+    double2 x[4];
+#pragma unroll
+    for (int part = 0; part < 4; ++part) x[part] = lds_v2(a_ti + BUF + part * CS * 8);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] *= pr;
+    const bool own_col = (tj == tk), own_row = (ti == tk);
+    v[KK] = own_col ? 1.0 - pr : v[KK];            // column k of its owners becomes c/d  (see sweep_step)
+    {
+        double& xk = (KK & 1) ? x[KK >> 1].y : x[KK >> 1].x;
+        xk = own_row ? xk - 1.0 : xk;              // row k of its owners becomes c/d
+    }
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            A[2 * part][c] = fma(-x[part].x, v[c], A[2 * part][c]);
+            A[2 * part + 1][c] = fma(-x[part].y, v[c], A[2 * part + 1][c]);
+        }
+    }
+    A[KK][KK] = (own_col && own_row) ? -pr : A[KK][KK];
+    if (!LAST) {
+        const int tkn = (KK < 7) ? tk : tk + 1;
+        publish_bf<(KK + 1) & 7>(A, active & (tj == tkn), active & (ti == tkn), a_ti + NBUF, a_tj + NBUF, piv_a + (k + 1) * 8,
+                                 pbuf_a + ((KK + 1) & 1) * 8);
+    }
+    GROUP_SYNC();
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -142,7 +234,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid, int 
     return s;
 }
 
-template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT>
+template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT, bool BF = false>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
 small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     extern __shared__ __align__(16) double smem_all[];
@@ -229,6 +321,34 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     // ---- publish column 0, then N sweep steps ----------------------------------------------------
     publish<0>(A, ti, tj, 0, 0, T, cbuf, pbuf, piv, active);
     GROUP_SYNC();
+    if (BF) {
+        const unsigned cb_a = (unsigned)__cvta_generic_to_shared(cbuf);
+        const unsigned a_ti = cb_a + ti * 16, a_tj = cb_a + tj * 16;
+        const unsigned pbuf_a = (unsigned)__cvta_generic_to_shared(pbuf), piv_a = (unsigned)__cvta_generic_to_shared(piv);
+        const int act = active ? 1 : 0;
+        const int full = N >> 3;   // tiles whose eight pivots are all < N: no exit tests inside (publishing column N is harmless)
+        for (int tk = 0; tk < full; ++tk) {
+            const int k0 = tk * 8;
+            sweep_step_bf<0, false>(A, ti, tj, tk, k0 + 0, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<1, false>(A, ti, tj, tk, k0 + 1, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<2, false>(A, ti, tj, tk, k0 + 2, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<3, false>(A, ti, tj, tk, k0 + 3, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<4, false>(A, ti, tj, tk, k0 + 4, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<5, false>(A, ti, tj, tk, k0 + 5, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<6, false>(A, ti, tj, tk, k0 + 6, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            sweep_step_bf<7, false>(A, ti, tj, tk, k0 + 7, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+        }
+        {   // the remaining N % 8 pivots (the border row N and the padding are never pivots)
+            const int tk = full, k0 = full * 8, rem = N - k0;
+            if (rem > 0) sweep_step_bf<0, false>(A, ti, tj, tk, k0 + 0, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            if (rem > 1) sweep_step_bf<1, false>(A, ti, tj, tk, k0 + 1, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            if (rem > 2) sweep_step_bf<2, false>(A, ti, tj, tk, k0 + 2, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            if (rem > 3) sweep_step_bf<3, false>(A, ti, tj, tk, k0 + 3, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            if (rem > 4) sweep_step_bf<4, false>(A, ti, tj, tk, k0 + 4, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            if (rem > 5) sweep_step_bf<5, false>(A, ti, tj, tk, k0 + 5, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+            if (rem > 6) sweep_step_bf<6, false>(A, ti, tj, tk, k0 + 6, a_ti, a_tj, pbuf_a, piv_a, act, gid, nthreads);
+        }
+    } else
     for (int tk = 0; tk < T; ++tk) {
         const int k0 = tk * 8;
         if (k0 >= N) break;
@@ -387,7 +507,20 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
     const int ntiles = T * (T + 1) / 2;
     const int threads = (ntiles + 31) / 32 * 32;
     const size_t sm = smem_bytes(T, b.want_grad);
-    static const int variant = getenv("GPCC_SMALL_VARIANT") ? atoi(getenv("GPCC_SMALL_VARIANT")) : 1;
+    static const int variant_env = getenv("GPCC_SMALL_VARIANT") ? atoi(getenv("GPCC_SMALL_VARIANT")) : -1;
+    static int nsm = 0;
+    if (nsm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // Default: pick the occupancy variant by batch size (measured on B200, profiles/small_sweep_variants_r1.log).
+    //   N <= 111 (128 threads): three CTAs per SM are 8 % faster once every SM has three (32.7 vs 35.6 us per evaluation
+    //   and SM), but slower when the batch leaves SMs with one or two (82 vs 65 us at one CTA per SM);
+    //   N <= 151 (192 threads): a CTA that is alone on its SM runs faster with 255 registers and no spills (101 vs 122 us),
+    //   two co-resident CTAs at 168 registers win as soon as there is more than one evaluation per SM (134 vs 188 us for two).
+    int variant = variant_env;
+    if (variant < 0) variant = (threads <= 128) ? (b.M >= 3 * nsm ? 2 : 1) : (b.M <= nsm ? 0 : 1);
     const int gd = (int)((sm + 15) / 16 * 2);   // doubles per group, 16-byte aligned
     if (threads <= 128) {
         if (variant == 3) {   // three matrices per CTA: 12 warps, 3 per scheduler
@@ -407,6 +540,10 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
         auto kfn = small_sweep_kernel<KID, 384, 1, 2>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (int)((smem_bytes(19, 1) + 15) / 16 * 2));
         kfn<<<(b.M + 1) / 2, 2 * threads, (size_t)2 * gd * 8, s>>>(p, b, T, gd);
+    } else if (threads <= 192 && variant == 4) {   // branch-free step
+        auto kfn = small_sweep_kernel<KID, 192, 2, 1, true>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
+        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
     } else if (threads <= 192 && variant == 1) {
         auto kfn = small_sweep_kernel<KID, 192, 2, 1>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
