@@ -59,38 +59,40 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, d
     EvalSlot& q = s.slot[slot];
     const int L = p->L;
     CUDA_TRY(cudaSetDevice(s.dev));
-    CUDA_TRY(cudaMemcpyAsync(q.delays.d, q.delays.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(q.alpha.d, q.alpha.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(q.rho.d, q.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    static const int one_stream = getenv("GPCC_ONE_STREAM") ? atoi(getenv("GPCC_ONE_STREAM")) : 0;
+    cudaStream_t stream = (slot == 1 && p->small_path && !one_stream) ? s.stream2 : s.stream;
+    CUDA_TRY(cudaMemcpyAsync(q.delays.d, q.delays.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(q.alpha.d, q.alpha.h, (size_t)M * L * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(q.rho.d, q.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, stream));
     EvalBatch b;
     b.M = M; b.delays = q.delays.d; b.alpha = q.alpha.d; b.rho = q.rho.d; b.want_grad = want_grad;
     b.ll = q.ll.d; b.grad = q.grad.d; b.info = q.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a; b.mode_postb = mode_postb;
     const bool prof = p->ctx->profiling;
     q.M = M; q.want_grad = want_grad; q.timed = false;
     if (p->small_path) {
-        if (prof) CUDA_TRY(cudaEventRecord(q.ev0, s.stream));
+        if (prof) CUDA_TRY(cudaEventRecord(q.ev0, stream));
         static const int use_dmma = getenv("GPCC_SMALL_DMMA") ? atoi(getenv("GPCC_SMALL_DMMA")) : 0;
         static const int use_block = getenv("GPCC_SMALL_BLOCK") ? atoi(getenv("GPCC_SMALL_BLOCK")) : 0;
         static const int use_frag = getenv("GPCC_SMALL_FRAG") ? atoi(getenv("GPCC_SMALL_FRAG")) : 0;
-        if (use_frag && small_frag_supports(p->N)) CUDA_TRY(small_frag_launch(p->pd[di].dp, b, s.stream));
-        else if (use_block && small_block_supports(p->N)) CUDA_TRY(small_block_launch(p->pd[di].dp, b, s.stream));
-        else if (use_dmma && small_dmma_supports(p->N)) CUDA_TRY(small_dmma_launch(p->pd[di].dp, b, s.stream));
-        else CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, s.stream));
-        if (prof) CUDA_TRY(cudaEventRecord(q.ev1, s.stream));
+        if (use_frag && small_frag_supports(p->N)) CUDA_TRY(small_frag_launch(p->pd[di].dp, b, stream));
+        else if (use_block && small_block_supports(p->N)) CUDA_TRY(small_block_launch(p->pd[di].dp, b, stream));
+        else if (use_dmma && small_dmma_supports(p->N)) CUDA_TRY(small_dmma_launch(p->pd[di].dp, b, stream));
+        else CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, stream));
+        if (prof) CUDA_TRY(cudaEventRecord(q.ev1, stream));
         q.timed = prof;
         s.launches += 1;
     } else {
         LargeTimings lt;
-        CUDA_TRY(large_eval(p->pd[di].dp, b, s.large, s.stream, prof, &lt));
+        CUDA_TRY(large_eval(p->pd[di].dp, b, s.large, stream, prof, &lt));
         s.launches += lt.launches;
         s.ms_assembly += lt.ms_assembly; s.ms_factor += lt.ms_factor; s.ms_gradreduce += lt.ms_gradreduce;
         s.ms_eval += lt.ms_assembly + lt.ms_factor + lt.ms_gradreduce;
     }
-    CUDA_TRY(cudaMemcpyAsync(q.ll.h, q.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(q.ll.h, q.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (want_grad)
-        CUDA_TRY(cudaMemcpyAsync(q.grad.h, q.grad.d, (size_t)M * (L + 1) * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(q.info.h, q.info.d, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaEventRecord(q.done, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(q.grad.h, q.grad.d, (size_t)M * (L + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(q.info.h, q.info.d, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(q.done, stream));
     return 0;
 }
 
@@ -100,9 +102,13 @@ int gpcc::finish_eval(gpcc_problem* p, int di, int slot) {
     CUDA_TRY(cudaSetDevice(s.dev));
     CUDA_TRY(cudaEventSynchronize(q.done));
     if (q.timed) {
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, q.ev0, q.ev1));
-        s.ms_eval += ms;
+        // union of the launch intervals: the two slots run on two streams and overlap in their tails
+        float t0 = 0, t1 = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t0, s.origin, q.ev0));
+        CUDA_TRY(cudaEventElapsedTime(&t1, s.origin, q.ev1));
+        const double from = std::max((double)t0, s.busy_end_ms);
+        if (t1 > from) s.ms_eval += t1 - from;
+        s.busy_end_ms = std::max(s.busy_end_ms, (double)t1);
     }
     s.evals += q.M;
     if (q.want_grad) s.evals_grad += q.M;
@@ -135,6 +141,14 @@ void reset_stats(gpcc_ctx* ctx) {
     for (auto& s : ctx->ds) {
         s.ms_eval = s.ms_assembly = s.ms_factor = s.ms_gradreduce = 0;
         s.launches = s.evals = s.evals_grad = 0;
+        if (s.origin) {   // new time zero (float milliseconds lose resolution far from the origin)
+            cudaSetDevice(s.dev);
+            cudaStreamSynchronize(s.stream);
+            cudaStreamSynchronize(s.stream2);
+            cudaEventRecord(s.origin, s.stream);
+            cudaEventSynchronize(s.origin);
+            s.busy_end_ms = 0;
+        }
     }
 }
 
@@ -224,7 +238,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
     // While the kernel of one half runs, the host feeds the results of the other half to its L-BFGS state machines
     // and packs that half's next trial points (the fused small-N path only; one slot for the tiled path, whose
     // workspace is shared and whose host share is negligible).
-    constexpr size_t MERGE_BELOW = 1024;   // fewer active candidates than this: one batch per round (latency bound)
+    static const size_t MERGE_BELOW = getenv("GPCC_MERGE_BELOW") ? (size_t)atol(getenv("GPCC_MERGE_BELOW")) : 1024;   // fewer active candidates than this: one batch per round (latency bound)
     int G = (p->small_path && (size_t)m >= MERGE_BELOW) ? 2 : 1;
     std::vector<int> active[2];
     for (int c = 0; c < m; ++c)
@@ -380,6 +394,10 @@ int gpcc_ctx_create(int ndev, const int* dev_ids, gpcc_ctx** out) {
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaEventCreate(&s.origin));
+        CUDA_TRY(cudaEventRecord(s.origin, s.stream));
+        CUDA_TRY(cudaEventSynchronize(s.origin));
         for (auto& q : s.slot) {
             CUDA_TRY(cudaEventCreate(&q.ev0));
             CUDA_TRY(cudaEventCreate(&q.ev1));
@@ -404,6 +422,8 @@ int gpcc_ctx_destroy(gpcc_ctx* ctx) {
         }
         large_workspace_release(s.large);
         if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.stream2) cudaStreamDestroy(s.stream2);
+        if (s.origin) cudaEventDestroy(s.origin);
     }
     delete ctx;
     return 0;

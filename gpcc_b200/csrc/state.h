@@ -45,8 +45,11 @@ struct DevBuf {   // growable device buffer + pinned host mirror
 };
 
 // Staging of one in-flight evaluation batch.  Two slots per device let the host-side L-BFGS bookkeeping of one
-// half of the candidates overlap with the kernel of the other half (all work is issued on ONE stream, so kernels
-// never overlap each other and the per-kernel CUDA-event timings stay exact).
+// half of the candidates overlap with the kernel of the other half.  On the fused small-N path each slot has its own
+// stream: the CTAs of the next batch start on the SMs that the tail of the running one leaves idle (a batch ends with
+// a partial wave, and there are ~200 batches per fitted grid).  Per-launch CUDA-event times therefore overlap in
+// those tails, so the kernel time reported in the statistics is the length of the UNION of the launch intervals
+// (all event times are taken relative to one origin event per device).
 struct EvalSlot {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
     DevBuf<double> delays, alpha, rho, ll, grad;
@@ -58,6 +61,9 @@ struct EvalSlot {
 struct DeviceState {
     int dev = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // slot 1 of the fused small-N path
+    cudaEvent_t origin = nullptr;     // time zero of the kernel-busy accounting (re-recorded when the statistics are reset)
+    double busy_end_ms = 0;           // end of the last kernel interval counted so far, relative to `origin`
     EvalSlot slot[2];
     DevBuf<double> post_ll, post_prior, post_out;   // persistent staging of the posterior kernel (no cudaMalloc/cudaFree per call)
     LargeWorkspace large;     // tiled large-N path (large_path.cu)
