@@ -355,8 +355,12 @@ def gpcc(tarray, yarray, stdarray, *, kernel, delays, iterations, seed=1, number
         if ytest is not None:
             ll, info = p.predict_loglik(delays, alpha, rho, ttest, ytest, stest)
             if info != 0:
-                raise GpccError("predictive covariance not positive definite (the reference repairs it with "
-                                "MiscUtil.nearestposdef, :331; do that on the host with the full covariance)")
+                # PosDefException branch of the reference (:323-341): nearestposdef(Sigma; minimumeigenvalue=1e-6), i.e.
+                # eigenvalues clamped from below (src/UNUSED/gpcc.jl:294-300 spells it out), then logpdf.  The reference does
+                # this repair in host code (MiscUtil) on an exceptional path; mu and Sigma still come from the device.
+                mu_, _, S_, _ = p.predict(delays, alpha, rho, ttest, full_cov=True)
+                S_ = S_ + np.diag(np.concatenate([_f64(a) for a in stest]) ** 2)
+                return repaired_logpdf(mu_, S_, np.concatenate([_f64(a) for a in ytest]))
             return ll
         if len(ttest) > 0 and np.ndim(ttest[0]) > 0:                    # Vector{Vector}: (mu, Sigma) (:259-289)
             mu_, _, S_, _ = p.predict(delays, alpha, rho, ttest, full_cov=True)
@@ -380,3 +384,53 @@ def gpccgrid(tarray, yarray, stdarray, candidatedelays, *, kernel, iterations, s
         theta0 = initial_solutions(yarray, seed, 1, initialrandom, rhomin, rhomax)[0][0]
     return p.grid_posterior(candidatedelays, theta0, iterations=iterations, rhomin=rhomin, rhomax=rhomax,
                             logprior=logprior)
+
+
+def repaired_logpdf(mu, Sigma, y, minimumeigenvalue=1e-6):
+    """logpdf(MvNormal(mu, nearestposdef(Sigma; minimumeigenvalue)), y): the PosDefException branch of the reference's test
+    likelihood (gpccfixdelay_marginaliseb.jl:323-341; the eigenvalue clamp is spelled out in src/UNUSED/gpcc.jl:294-300)."""
+    S = 0.5 * (np.asarray(Sigma, dtype=np.float64) + np.asarray(Sigma, dtype=np.float64).T)
+    w, V = np.linalg.eigh(S)
+    S = (V * np.maximum(w, minimumeigenvalue)) @ V.T
+    c = np.linalg.cholesky(0.5 * (S + S.T))
+    z = np.linalg.solve(c, np.asarray(y, dtype=np.float64) - np.asarray(mu, dtype=np.float64))
+    return float(-0.5 * (len(z) * math.log(2.0 * math.pi) + 2.0 * np.sum(np.log(np.diag(c))) + z @ z))
+
+
+def cv_folds(nper, numberoffolds=5, seedcv=1):
+    """Fold assignment per band, each band partitioned on its own with seed seedcv + b (src/UNUSED/performcv.jl:66).  The
+    reference takes its partitions from MiscUtil.CVindices (Julia RNG); a numpy permutation dealt round robin stands in
+    for it here, and callers (the Julia shim) can pass their own `folds` instead."""
+    folds = []
+    for b, n in enumerate(nper):
+        perm = np.random.default_rng(seedcv + b + 1).permutation(n)
+        f = np.empty(n, dtype=np.int64)
+        f[perm] = np.arange(n) % numberoffolds
+        folds.append(f)
+    return folds
+
+
+def performcv(tobs, yobs, sobs, *, delays, kernel, iterations=1, seedcv=1, numberofrestarts=1, initialrandom=1,
+              numberoffolds=5, rhomin=0.1, rhomax=20.0, folds=None, theta0=None, ctx=None, out=None):
+    """K-fold cross-validation of the GPCC model at fixed delays, the retired consumer of `gpcc` + `pred(t, y, sigma)` in
+    src/UNUSED/performcv.jl:41-139: per fold, fit on the training part and evaluate the test log-likelihood
+    of the held-out part, both on the device.  Returns the vector of fold scores (to be fed to `getprobabilities`).
+    `theta0[k]`: optional start set of fold k (restarts x draws x (L+1)), as in `gpcc`."""
+    out = out or sys.stdout
+    out.write("\nRunning CV with %d number of folds, random seed set to %d\n\n" % (numberoffolds, seedcv))       # :44
+    if not (len(tobs) == len(yobs) == len(sobs)) or any(not (len(a) == len(b_) == len(c)) for a, b_, c in zip(tobs, yobs, sobs)):
+        raise GpccError("tobs, yobs, sobs differ in shape")                                                       # :50-55
+    if folds is None:
+        folds = cv_folds([len(t) for t in tobs], numberoffolds, seedcv)
+    fitness = np.zeros(numberoffolds)
+    for k in range(numberoffolds):
+        tr = [np.asarray(f) != k for f in folds]
+        part = lambda arrs, masks: [_f64(a)[m] for a, m in zip(arrs, masks)]
+        te = [~m for m in tr]
+        out.write("\n--- fold %d train size is %d, test size is %d ---\n" % (k + 1, sum(int(m.sum()) for m in tr), sum(int(m.sum()) for m in te)))
+        pred = gpcc(part(tobs, tr), part(yobs, tr), part(sobs, tr), kernel=kernel, delays=delays, iterations=iterations,
+                    seed=seedcv, numberofrestarts=numberofrestarts, initialrandom=initialrandom, rhomin=rhomin, rhomax=rhomax,
+                    theta0=None if theta0 is None else theta0[k], ctx=ctx, verbose=False)[1]                      # @suppress gpcc(...)[2] (:101)
+        fitness[k] = pred(part(tobs, te), part(yobs, te), part(sobs, te))                                         # :104
+        out.write("\t perf for fold %d is %f\n" % (k + 1, fitness[k]))
+    return fitness

@@ -124,6 +124,105 @@ __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, in
     GROUP_SYNC();
 }
 
+// ---- two pivots per barrier (PAIR = true, even N) -----------------------------------------------------------------------
+// Columns k and k+1 of the symmetric matrix are published together, as they stand before step k.  Every thread rebuilds
+// the entries of column k+1 it needs AFTER step k itself (c'_i = c_{k+1,i} - c_{k,i} m with m = c_{k,k+1} / d_k: the very
+// FMA the owner of that entry performs in step k, so the values are identical), forms d'_{k+1} = d_{k+1} - c_{k,k+1} m and
+// its reciprocal, and applies the two rank-1 steps back to back, two tile rows at a time.  The arithmetic is that of the
+// rank-1 kernel (no 2x2 pivot block is inverted); what halves is everything paid once per barrier: the barrier itself, the
+// shared-memory round trip behind it, the divergent owner paths of `publish` and their branches, and the reciprocal chain.
+template <int KKN>
+__device__ __forceinline__ void publish2(const double (&A)[8][8], int ti, int tj, int tkn, int kn, double* nb, double* pslot,
+                                         double* piv, bool active) {
+    const bool pc = active && (tj == tkn), prw = active && (ti == tkn);
+    if (!__any_sync(0xffffffffu, pc || prw)) return;
+    if (pc) {
+        double* da = nb + 2 * ti;
+        double* db = da + VLEN;
+        if (prw) {  // diagonal tile: below the diagonal from the column, above it from the row
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                da[(r >> 1) * CS + (r & 1)] = (r >= KKN) ? A[r][KKN] : A[KKN][r];
+                db[(r >> 1) * CS + (r & 1)] = (r >= KKN + 1) ? A[r][KKN + 1] : A[KKN + 1][r];
+            }
+            const double d = A[KKN][KKN];
+            piv[kn] = d;
+            *pslot = 1.0 / d;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                da[(r >> 1) * CS + (r & 1)] = A[r][KKN];
+                db[(r >> 1) * CS + (r & 1)] = A[r][KKN + 1];
+            }
+        }
+    } else if (prw) {
+        double* da = nb + 2 * tj;
+        double* db = da + VLEN;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            da[(c >> 1) * CS + (c & 1)] = A[KKN][c];
+            db[(c >> 1) * CS + (c & 1)] = A[KKN + 1][c];
+        }
+    }
+}
+
+template <int KK>   // KK even: pivots k = 8 tk + KK and k + 1
+__device__ __forceinline__ void pair_step(double (&A)[8][8], int ti, int tj, int tk, int k, int N, double* cbuf, double* pbuf,
+                                          double* piv, bool active, int tid, int gid, int nthreads) {
+    const int par = (k >> 1) & 1;
+    const double* ca = cbuf + par * 2 * VLEN;
+    const double* cq = ca + VLEN;
+    double vA[8], vB[8];
+    load8(ca, tj, 0, vA);
+    load8(cq, tj, 0, vB);
+    const double pr = pbuf[par];
+    const int ik1 = ((KK + 1) >> 1) * CS + tk * 2 + 1;     // chunk index of row k + 1
+    const double ckk1 = ca[ik1], dB = cq[ik1];
+    const double m = ckk1 * pr;
+    const double dBp = fma(-ckk1, m, dB);                   // pivot k+1 after step k
+    const double prB = 1.0 / dBp;
+    if (tid == 0) piv[k + 1] = dBp;
+    const bool own_col = (tj == tk), own_row = (ti == tk);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double xa = vA[c];
+        if (c == KK) xa = own_col ? xa - 1.0 : xa;         // the row-k value of step k for index (tj, c)
+        vB[c] = fma(-xa, m, vB[c]) * prB;                   // column k+1 after step k, scaled by 1/d'
+        vA[c] *= pr;
+    }
+    vA[KK] = own_col ? 1.0 - pr : vA[KK];
+    vB[KK + 1] = own_col ? 1.0 - prB : vB[KK + 1];
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+        double2 xa = *reinterpret_cast<const double2*>(ca + part * CS + 2 * ti);
+        const double2 xb = *reinterpret_cast<const double2*>(cq + part * CS + 2 * ti);
+        if (part == (KK >> 1)) xa.x = own_row ? xa.x - 1.0 : xa.x;
+        double2 xp;
+        xp.x = fma(-xa.x, m, xb.x);
+        xp.y = fma(-xa.y, m, xb.y);
+        if (part == (KK >> 1)) xp.y = own_row ? xp.y - 1.0 : xp.y;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            A[2 * part][c] = fma(-xa.x, vA[c], A[2 * part][c]);
+            A[2 * part + 1][c] = fma(-xa.y, vA[c], A[2 * part + 1][c]);
+        }
+        if (part == (KK >> 1)) A[KK][KK] = (own_col && own_row) ? -pr : A[KK][KK];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            A[2 * part][c] = fma(-xp.x, vB[c], A[2 * part][c]);
+            A[2 * part + 1][c] = fma(-xp.y, vB[c], A[2 * part + 1][c]);
+        }
+        if (part == (KK >> 1)) A[KK + 1][KK + 1] = (own_col && own_row) ? -prB : A[KK + 1][KK + 1];
+    }
+    const int kn = k + 2;
+    if (kn < N) {
+        double* nb = cbuf + (par ^ 1) * 2 * VLEN;
+        if (KK < 6) publish2<(KK + 2) & 7>(A, ti, tj, tk, kn, nb, pbuf + (par ^ 1), piv, active);
+        else        publish2<0>(A, ti, tj, tk + 1, kn, nb, pbuf + (par ^ 1), piv, active);
+    }
+    GROUP_SYNC();
+}
+
 // ---- branch-free form of the step (BF = true) -------------------------------------------------------------------------
 // Measured on B200 (profiles/README.md, round-1 session 2): a warp issues in order and a lone warp pays ~25-30 cycles for
 // every taken branch and ~30 for every shared-memory round trip, so with two or three warps per scheduler the eight
@@ -234,7 +333,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid, int 
     return s;
 }
 
-template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT, bool BF = false>
+template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT, bool BF = false, bool PAIR = false>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
 small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     extern __shared__ __align__(16) double smem_all[];
@@ -259,7 +358,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     double* sbv = av + VLEN;        // Sigma_b[band(i)]                         (chunk layout)
     double* dadd = sbv + VLEN;      // sigma_i^2                                (chunk layout)
     double* cbuf = dadd + VLEN;     // 2 x broadcast column                     (chunk layout)
-    double* piv = cbuf + 2 * VLEN;  // pivots                                   (natural)
+    double* piv = cbuf + 4 * VLEN;  // pivots (cbuf: 2 buffers x 2 columns for the two-pivot step)   (natural)
     double* abuf = piv + VLEN;      // residual r, later a = K~^-1 r            (chunk layout)
     double* pbuf = abuf + VLEN;     // 2 pivot reciprocals (+2 pad)
     double* red = pbuf + 4;         // 64 reduction slots
@@ -319,6 +418,18 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     GROUP_SYNC();   // everyone has read abuf/tsh before cbuf traffic starts (abuf is reused later)
 
     // ---- publish column 0, then N sweep steps ----------------------------------------------------
+    if (PAIR) {   // N even (host dispatch)
+        publish2<0>(A, ti, tj, 0, 0, cbuf, pbuf, piv, active);
+        GROUP_SYNC();
+        for (int tk = 0; tk < T; ++tk) {
+            const int k0 = tk * 8;
+            if (k0 >= N) break;
+            pair_step<0>(A, ti, tj, tk, k0 + 0, N, cbuf, pbuf, piv, active, tid, gid, nthreads); if (k0 + 2 >= N) break;
+            pair_step<2>(A, ti, tj, tk, k0 + 2, N, cbuf, pbuf, piv, active, tid, gid, nthreads); if (k0 + 4 >= N) break;
+            pair_step<4>(A, ti, tj, tk, k0 + 4, N, cbuf, pbuf, piv, active, tid, gid, nthreads); if (k0 + 6 >= N) break;
+            pair_step<6>(A, ti, tj, tk, k0 + 6, N, cbuf, pbuf, piv, active, tid, gid, nthreads);
+        }
+    } else {
     publish<0>(A, ti, tj, 0, 0, T, cbuf, pbuf, piv, active);
     GROUP_SYNC();
     if (BF) {
@@ -360,6 +471,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
         sweep_step<5>(A, ti, tj, tk, k0 + 5, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 6 >= N) break;
         sweep_step<6>(A, ti, tj, tk, k0 + 6, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 7 >= N) break;
         sweep_step<7>(A, ti, tj, tk, k0 + 7, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads);
+    }
     }
 
     // ---- log-determinant, info, quadratic form ---------------------------------------------------
@@ -498,7 +610,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
 
 size_t smem_bytes(int T, int want_grad) {
     const int Np = T * TS;
-    size_t doubles = (size_t)VLEN * 8 + 4 + 64 + (want_grad ? (size_t)T * T * 8 : 0);
+    size_t doubles = (size_t)VLEN * 10 + 4 + 64 + (want_grad ? (size_t)T * T * 8 : 0);
     return doubles * sizeof(double) + (size_t)Np * sizeof(int) + 16;
 }
 
@@ -540,6 +652,10 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
         auto kfn = small_sweep_kernel<KID, 384, 1, 2>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (int)((smem_bytes(19, 1) + 15) / 16 * 2));
         kfn<<<(b.M + 1) / 2, 2 * threads, (size_t)2 * gd * 8, s>>>(p, b, T, gd);
+    } else if (threads <= 192 && variant == 5 && (p.N % 2) == 0) {   // two pivots per barrier
+        auto kfn = small_sweep_kernel<KID, 192, 2, 1, false, true>;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
+        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
     } else if (threads <= 192 && variant == 4) {   // branch-free step
         auto kfn = small_sweep_kernel<KID, 192, 2, 1, true>;
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));

@@ -26,4 +26,4 @@ from .model import (Problem, makepositive, invmakepositive, transformbetween,  #
                     invtransformbetween)
 from .posterior import getprobabilities, uniformpriordelay, Uniform           # noqa: F401
 from .simulate import simulatedata, simulatetwolightcurves, simulatethreelightcurves, synthetic_bands  # noqa: F401
-from .fit import gpcc, initial_solutions                                       # noqa: F401
+from .fit import gpcc, initial_solutions, performcv, cv_folds                  # noqa: F401

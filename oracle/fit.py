@@ -148,3 +148,35 @@ def gpcc(tarray, yarray, stdarray, *, kernel, delays, iterations, seed=1, number
     if return_info:
         return out + (dict(nfev=nfev[0], theta=theta_opt),)
     return out
+
+
+def cv_folds(nper, numberoffolds=5, seedcv=1):
+    """Fold assignment per band, each band partitioned on its own with seed seedcv + b (UNUSED/performcv.jl:66).  The
+    reference takes its partitions from MiscUtil.CVindices (Julia RNG, not reproducible here): a numpy permutation dealt
+    round robin stands in for it, and callers can pass their own folds instead."""
+    folds = []
+    for b, n in enumerate(nper):
+        perm = np.random.default_rng(seedcv + b + 1).permutation(n)
+        f = np.empty(n, dtype=np.int64)
+        f[perm] = np.arange(n) % numberoffolds
+        folds.append(f)
+    return folds
+
+
+def performcv(tobs, yobs, sobs, *, delays, kernel, iterations=1, seedcv=1, numberofrestarts=1, initialrandom=1,
+              numberoffolds=5, rhomin=0.1, rhomax=20.0, folds=None, optimizer="lbfgs", theta0=None):
+    """K-fold cross-validation of the GPCC model at fixed delays (UNUSED/performcv.jl:41-139): fit on the training part,
+    test log-likelihood pred(ttest, ytest, stest) on the held-out part; returns the vector of fold scores."""
+    if folds is None:
+        folds = cv_folds([len(t) for t in tobs], numberoffolds, seedcv)
+    fitness = np.zeros(numberoffolds)
+    for k in range(numberoffolds):
+        tr = [np.asarray(f) != k for f in folds]
+        sel = lambda arrs, mask_list: [np.asarray(a, dtype=np.float64)[m] for a, m in zip(arrs, mask_list)]
+        te = [~m for m in tr]
+        th = None if theta0 is None else theta0[k]
+        r = gpcc(sel(tobs, tr), sel(yobs, tr), sel(sobs, tr), kernel=kernel, delays=delays, iterations=iterations, seed=seedcv,
+                 numberofrestarts=numberofrestarts, initialrandom=initialrandom, rhomin=rhomin, rhomax=rhomax,
+                 optimizer=optimizer, theta0=th)
+        fitness[k] = r[1](sel(tobs, te), sel(yobs, te), sel(sobs, te))
+    return fitness

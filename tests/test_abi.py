@@ -111,3 +111,20 @@ def test_initial_solutions_follow_reference_draw_order():
     assert np.all(th[0, :, 2] == th[0, 0, 2])                                                # rho0 shared by the draws (:196)
     th3, r3 = gpcc_b200.initial_solutions(y, seed=1, numberofrestarts=4, initialrandom=2, rhomin=0.1, rhomax=20.0)
     assert np.allclose(np.diff(np.log(r3)), np.log(r3[1] / r3[0]))                           # log-spaced grid (:172)
+
+
+def test_repaired_logpdf_matches_the_reference_recipe():
+    """Host-side repair of a predictive covariance that is not positive definite (reference :323-341): eigenvalues clamped
+    at 1e-6, then the Gaussian log-density -- checked against the oracle's restatement of the same branch."""
+    import numpy as np
+    import gpcc_b200
+    rg = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rg.normal(size=(6, 6)))
+    S = (Q * np.array([2.0, 1.0, 0.5, 1e-3, -1e-9, -0.2])) @ Q.T          # indefinite
+    mu, y = rg.normal(size=6), rg.normal(size=6)
+    got = gpcc_b200.api.repaired_logpdf(mu, S, y)
+    w, V = np.linalg.eigh(0.5 * (S + S.T))
+    Sr = (V * np.maximum(w, 1e-6)) @ V.T
+    sign, logdet = np.linalg.slogdet(Sr)
+    ref = -0.5 * (6 * np.log(2 * np.pi) + logdet + (y - mu) @ np.linalg.solve(Sr, y - mu))
+    assert sign > 0 and abs(got - ref) < 1e-9 * abs(ref)

@@ -141,6 +141,36 @@ def test_cfg1_single_fit_matches_oracle(ctx, capsys):
     assert info == 0 and abs(tl - float(g["test_loglik"])) / abs(float(g["test_loglik"])) < PRED_RTOL
 
 
+def test_test_likelihood_with_duplicated_test_times(ctx):
+    """pred(ttest, ytest, sigmatest) with a duplicated test time and zero test noise: only the 1e-8 jitter (:279) keeps the
+    predictive covariance positive definite; device and oracle must agree on this badly conditioned case as well."""
+    g = load_golden("fit_cfg1_cfg2")
+    tt = [np.array([3.0, 3.0, 9.0]), np.array([4.0, 12.0])]
+    yt = [np.array([6.1, 6.1, 5.5]), np.array([14.0, 13.0])]
+    st = [np.zeros(3), np.array([0.5, 0.5])]
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    got, info = p.predict_loglik(g["truedelays"], g["alpha"], float(g["rho"]), tt, yt, st)
+    ref = oracle.Problem(g["tb"], g["yb"], g["sb"], "matern32").predict_loglik(g["truedelays"], g["alpha"], float(g["rho"]), tt, yt, st)
+    assert info == 0 and np.isfinite(got) and abs(got - ref) / abs(ref) < 1e-4      # cond ~ 1e10: agreement to ~1e-6 is all FP64 gives
+
+
+def test_cross_validation_driver_matches_oracle(ctx):
+    """performcv (src/UNUSED/performcv.jl:41-139): fold-wise fit + held-out test log-likelihood, same folds and
+    start points on both sides."""
+    import io
+    t, y, s, d = gpcc_b200.simulatetwolightcurves()
+    folds = gpcc_b200.cv_folds([len(a) for a in t], 3, 1)
+    th = []
+    for k in range(3):
+        ytr = [np.asarray(a)[np.asarray(f) != k] for a, f in zip(y, folds)]
+        th.append(gpcc_b200.initial_solutions(ytr, 1, 1, 3, 0.1, 20.0)[0])
+    got = gpcc_b200.performcv(t, y, s, delays=d, kernel=gpcc_b200.matern32, iterations=500, numberoffolds=3, folds=folds,
+                              theta0=th, ctx=ctx, out=io.StringIO())
+    ref = oracle.performcv(t, y, s, delays=d, kernel="matern32", iterations=500, numberoffolds=3, folds=folds, theta0=th)
+    assert got.shape == (3,) and np.all(np.isfinite(got))
+    assert np.max(np.abs(got - ref)) < 1e-5 * np.max(np.abs(ref))      # two optimisers, same optimum: test logL to ~1e-6
+
+
 def test_cfg2_grid_posterior_matches_oracle(ctx):
     g = load_golden("fit_cfg1_cfg2")
     p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
@@ -355,6 +385,8 @@ def test_prior_with_minus_infinity_and_iteration_cap_zero(ctx):
     {"GPCC_SMALL_FRAG": "1"},                                  # small_frag.cu: fragment layout, DMMA panel + update, helper warp
     {"GPCC_SMALL_FRAG": "1", "GPCC_FRAG_NMAT": "1"},
     {"GPCC_SMALL_VARIANT": "3"},                               # small_sweep.cu with several matrices per CTA
+    {"GPCC_SMALL_VARIANT": "4"},                               #                with the straight-line (predicated) step
+    {"GPCC_SMALL_VARIANT": "5"},                               #                with two pivots per barrier
 ], ids=lambda d: "+".join(f"{k[5:]}={v}" for k, v in d.items()))
 def test_experimental_fused_kernels_agree(ctx, switch):
     """The alternative small-N evaluators are off by default because none of them beats the rank-1 DFMA sweep yet
