@@ -47,7 +47,7 @@ namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 constexpr int MAX_T = 25;      // 8 * 25 = 200 rows (N <= 199 as in small_sweep.cu); 325 tiles = 11 warps
-constexpr int MAX_THREADS = 512;   // 16 warps x 128 registers: registers are handed out four warps at a time
+constexpr int MAX_THREADS = 512;   // HELPER build: 16 warps x 128 registers (registers are handed out four warps at a time)
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -58,13 +58,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // generic pointer from scratch (S2R, S2UR, a dozen dependent IMADs) in front of each access, which is what made every
 // phase of the first version run at ~10 cycles per instruction.
 constexpr int SLOTS = 32;       // tiles per warp ...
-constexpr int REG_SLOTS = 20;   // ... of which this many live in registers (80 of the 128 a thread may use at 16 warps per
-                                // SM); the other twelve stay in shared memory and take one LDS.128 + STS.128 per block step.
-                                // With all 32 in registers ptxas keeps some of them in LOCAL memory instead, which is worse.
+// ... of which RS live in registers; the others stay in shared memory and take one LDS.128 + STS.128 per block step (with all
+// 32 in registers ptxas keeps some of them in LOCAL memory instead, which is worse).  Two builds of the kernel:
+//   HELPER = false: 6 tile warps per matrix at N = 150, one matrix per CTA, two CTAs per SM at 168 registers, RS = 28; the
+//                   look-ahead pivot factorisation runs on the tile warp that finished the pivot tile (its tiles parked);
+//   HELPER = true:  a seventh warp per matrix does the factorisation on a scheduler of its own; registers are granted four
+//                   warps at a time, so this means 16 warps x 128 registers per SM and RS = 20.
+template <bool HELPER> struct FragCfg { static constexpr int RS = HELPER ? 20 : 28; };
 constexpr int CHUNK = 4;        // consecutive tiles (row major over the lower triangle) dealt to a warp at a time: the
                                 // A operand of the update is reloaded only when the tile row changes
 constexpr unsigned O_W = 0, O_WT = 512, O_ZR = 1024, O_MISC = 1088, O_RED = 1152, O_DB = 1280, O_DN = 1792, O_RV = 2816;   // Dn: two buffers
 constexpr unsigned O_PIV = O_RV + 3072, O_TM = O_PIV + 2048;
+// from O_TM on: [nwarps][SLOTS - RS] memory tiles, (HELPER = false) [RS] parked tiles, descriptors, operand table, panels
 // from O_TM on (sizes depend on the launch): [nwarps][4] memory-resident tiles, [nwarps][32] scan descriptors (8 B),
 // [nwarps][32] update-operand offsets (8 B), then Zb, Zn, Cb[0], Cb[1] (pb = 512 Tpad bytes each)
 __device__ __forceinline__ uint2 lds64u(unsigned a) {
@@ -190,11 +195,11 @@ __device__ __forceinline__ void pivot_tile(unsigned gb, int k) {
     sts64(gb + O_MISC, lds64(gb + O_MISC) + qs);
 }
 
-// Tile s of the warp: registers for s < REG_SLOTS, shared memory (tm = this lane's pair of the warp's first memory tile)
-#define TILE_GET(s, v0, v1) do { if ((s) < REG_SLOTS) { v0 = acc[(s) < REG_SLOTS ? (s) : 0][0]; v1 = acc[(s) < REG_SLOTS ? (s) : 0][1]; } \
-                                 else { const double2 t_ = lds128(tm + ((s) - REG_SLOTS) * 512); v0 = t_.x; v1 = t_.y; } } while (0)
-#define TILE_PUT(s, v0, v1) do { if ((s) < REG_SLOTS) { acc[(s) < REG_SLOTS ? (s) : 0][0] = v0; acc[(s) < REG_SLOTS ? (s) : 0][1] = v1; } \
-                                 else sts128(tm + ((s) - REG_SLOTS) * 512, v0, v1); } while (0)
+// Tile s of the warp: registers for s < RS, shared memory (tm = this lane's pair of the warp's first memory tile)
+#define TILE_GET(s, v0, v1) do { if ((s) < RS) { v0 = acc[(s) < RS ? (s) : 0][0]; v1 = acc[(s) < RS ? (s) : 0][1]; } \
+                                 else { const double2 t_ = lds128(tm + ((s) - RS) * 512); v0 = t_.x; v1 = t_.y; } } while (0)
+#define TILE_PUT(s, v0, v1) do { if ((s) < RS) { acc[(s) < RS ? (s) : 0][0] = v0; acc[(s) < RS ? (s) : 0][1] = v1; } \
+                                 else sts128(tm + ((s) - RS) * 512, v0, v1); } while (0)
 
 // Scan descriptors of block step kw (kw = -1 before the first step), one per tile, written by the lane whose number is
 // the tile's slot: {address to take the final value from, address to copy the tile to} (0 = nothing to do).
@@ -216,7 +221,8 @@ __device__ __forceinline__ void write_descriptors(unsigned da, int mytile, int k
 }
 // The scan proper: one predicated 16-byte load and one predicated 16-byte store per tile, no branches for the tiles
 // in registers.
-__device__ __forceinline__ void scan_tiles(double (&acc)[REG_SLOTS][2], unsigned tm, unsigned dw, unsigned lane16) {
+template <int RS>
+__device__ __forceinline__ void scan_tiles(double (&acc)[RS][2], unsigned tm, unsigned dw, unsigned lane16) {
     // A warp issues in order and these accesses are ordered among themselves: descriptors are fetched eight at a time,
     // then the loads they select, then the stores, so that the latencies overlap instead of adding up.
 #pragma unroll
@@ -227,27 +233,28 @@ __device__ __forceinline__ void scan_tiles(double (&acc)[REG_SLOTS][2], unsigned
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int s = g + u;
-            if (s < REG_SLOTS) {
-                if (d[u].x) { const double2 v = lds128(d[u].x + lane16); acc[s < REG_SLOTS ? s : 0][0] = v.x; acc[s < REG_SLOTS ? s : 0][1] = v.y; }
+            if (s < RS) {
+                if (d[u].x) { const double2 v = lds128(d[u].x + lane16); acc[s < RS ? s : 0][0] = v.x; acc[s < RS ? s : 0][1] = v.y; }
             }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int s = g + u;
-            if (s < REG_SLOTS) {
-                if (d[u].y) sts128(d[u].y + lane16, acc[s < REG_SLOTS ? s : 0][0], acc[s < REG_SLOTS ? s : 0][1]);
+            if (s < RS) {
+                if (d[u].y) sts128(d[u].y + lane16, acc[s < RS ? s : 0][0], acc[s < RS ? s : 0][1]);
             } else if (d[u].x | d[u].y) {
-                const double2 v = lds128(d[u].x ? d[u].x + lane16 : tm + (s - REG_SLOTS) * 512);
-                if (d[u].x) sts128(tm + (s - REG_SLOTS) * 512, v.x, v.y);
+                const double2 v = lds128(d[u].x ? d[u].x + lane16 : tm + (s - RS) * 512);
+                if (d[u].x) sts128(tm + (s - RS) * 512, v.x, v.y);
                 if (d[u].y) sts128(d[u].y + lane16, v.x, v.y);
             }
         }
     }
 }
 
-template <int KID>
-__global__ void __launch_bounds__(MAX_THREADS, 1)
+template <int KID, bool HELPER>
+__global__ void __launch_bounds__(HELPER ? MAX_THREADS : 384, 1)
 small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int hw_per_group, int nmat, int smem_doubles_per_group) {
+    constexpr int RS = FragCfg<HELPER>::RS;
     extern __shared__ __align__(16) double smem_all[];
     const int N = p.N, L = p.L;
     const int Np = 8 * T;
@@ -255,16 +262,19 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
     // one with w % 4 == 3: its scalar FP64 chain (the pivot factorisation) then never queues behind the 16-cycle DMMAs
     // of a tile warp, which slows it four-fold (measured).  Slots left over exit at once.
     const int hwarp = (int)threadIdx.x >> 5, gid = hwarp / hw_per_group, hl = hwarp % hw_per_group;
-    const int ntw = (gthreads >> 5) - 1;
-    int role = ((hl & 3) == 3) ? ((hl == 3) ? ntw : -1) : (hl >> 2) * 3 + (hl & 3);
-    if (role > ntw || ((hl & 3) != 3 && role >= ntw)) role = -1;
+    const int ntw = (gthreads >> 5) - (HELPER ? 1 : 0);
+    int role = hl;
+    if (HELPER) {
+        role = ((hl & 3) == 3) ? ((hl == 3) ? ntw : -1) : (hl >> 2) * 3 + (hl & 3);
+        if (role > ntw || ((hl & 3) != 3 && role >= ntw)) role = -1;
+    }
     const int e = blockIdx.x * nmat + gid;
     if (role < 0 || e >= b.M) return;   // spare slots; a whole group without work: its named barriers are never used
     const int tid = role * 32 + ((int)threadIdx.x & 31);
     const bool next_group_exists = (gid + 1 < nmat) && (e + 1 < b.M);
     double* smem = smem_all + (size_t)gid * smem_doubles_per_group;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = (gthreads >> 5) - 1;   // tile warps; warp `nwarps` is the helper
-    const bool helper = (warp == nwarps);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = ntw;   // tile warps; with HELPER, warp `nwarps` is the helper
+    const bool helper = HELPER && (warp == nwarps);
     const int ntiles = T * (T + 1) / 2;
     const int lr = lane >> 2, lc = (lane & 3) * 2;   // this lane's row and first column inside a tile
 
@@ -272,9 +282,10 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
     const unsigned gb = (unsigned)__cvta_generic_to_shared(smem);   // shared-window address of this group
     const unsigned lane16 = 16u * lane;
     const unsigned ltr = 16u * (lc * 4 + (lr >> 1)) + 8u * (lr & 1);   // this lane's first element in the TRANSPOSED tile (second: + 64)
-    const unsigned odesc = O_TM + (unsigned)nwarps * (SLOTS - REG_SLOTS) * 512, otab = odesc + (unsigned)nwarps * 256;
+    const unsigned opark = O_TM + (unsigned)nwarps * (SLOTS - RS) * 512;   // (HELPER = false) [RS] tiles of the factoring warp
+    const unsigned odesc = opark + (HELPER ? 0u : (unsigned)RS * 512u), otab = odesc + (unsigned)nwarps * 256;
     const unsigned ozb = otab + (unsigned)nwarps * 256;
-    const unsigned tm = gb + O_TM + (unsigned)warp * (SLOTS - REG_SLOTS) * 512 + lane16;   // this lane's pair of the warp's first memory tile
+    const unsigned tm = gb + O_TM + (unsigned)warp * (SLOTS - RS) * 512 + lane16;   // this lane's pair of the warp's first memory tile
     const unsigned dw = gb + odesc + (unsigned)warp * 256, tw = gb + otab + (unsigned)warp * 256;
     double* Wb = smem + O_W / 8;        // [64] W = L^-1 row major, [64] W' row major
     double* misc = smem + O_MISC / 8;   // [0] quadratic form, [2] info (as int)
@@ -333,7 +344,7 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
     group_sync(gid, gthreads);
 
     // ---- assembly, eight tiles at a time through the staging buffer (keeps the exp code out of the unrolled part) ---
-    double acc[REG_SLOTS][2];
+    double acc[RS][2];
     if (!helper)   // (the helper warp has no tiles: its accumulators stay undefined and are never read)
 #pragma unroll
     for (int c = 0; c < SLOTS / 8; ++c) {
@@ -373,8 +384,13 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
         write_descriptors(dw + lane * 8, mytile, -1, 0u, gb + ozb + 2 * pb, gb);   // panel 0, pivot tile 0 -> Db, pivot tile 1 -> Dn
         __syncwarp();
         scan_tiles(acc, tm, dw, lane16);
+        if (!HELPER && warp == 0) {   // tile (0,0) is slot 0 of warp 0
+            __syncwarp();
+            if (lane == 0) pivot_tile(gb, 0);
+        }
     }
-    group_sync(gid, gthreads);
+    if (HELPER) group_sync(gid, gthreads);
+    int pw = (nwarps > 1) ? 1 : 0;   // (HELPER = false) warp that owns block k+1 of the panel in step k: (k+1) % nwarps
     if (helper) {
         // Look-ahead: while the tile warps run the trailing update of step k, the helper warp finishes the next pivot
         // tile (D - Z Z' with Z = block k+1 of this step's panel, two DMMAs) and ONE of its lanes factors it: Cholesky of
@@ -468,6 +484,25 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
         PROF_TL(3);
         if (k == 0 && next_group_exists) asm volatile("bar.arrive %0, %1;" ::"r"(8 + gid + 1), "r"(2 * gthreads) : "memory");
         write_descriptors(dw + lane * 8, mytile, k, cw, cn, gb);   // read back after the update (same warp: __syncwarp)
+        if (!HELPER) {
+            // Look-ahead without a helper warp: the tile warp that owns block k+1 of the panel finishes the next pivot tile
+            // (D - Z Z') and ONE of its lanes factors it while the other warps run their update; the factorisation needs
+            // the registers of a whole thread, so the warp's tiles are parked in shared memory meanwhile.
+            if (k + 1 < T && warp == pw) {
+                const double2 z = lds128(gb + ozb + (k + 1) * 512 + lane16);
+                double2 d = lds128(gb + O_DN + ((k + 1) & 1) * 512 + lane16);
+                dmma884(d.x, d.y, negd(z.x), z.x);
+                dmma884(d.x, d.y, negd(z.y), z.y);
+                sts128(gb + O_DB + lane16, d.x, d.y);
+#pragma unroll
+                for (int s = 0; s < RS; ++s) sts128(gb + opark + s * 512 + lane16, acc[s][0], acc[s][1]);
+                __syncwarp();
+                if (lane == 0) pivot_tile(gb, k + 1);
+#pragma unroll
+                for (int s = 0; s < RS; ++s) { const double2 v = lds128(gb + opark + s * 512 + lane16); acc[s][0] = v.x; acc[s][1] = v.y; }
+            }
+            pw = (pw + 1 == nwarps) ? 0 : pw + 1;
+        }
         PROF_TL(4);
         // bulk: A_ij -= Z_i Z_j' on every tile of the warp (tiles of row / column k are overwritten right after).
         // Operand addresses come from the warp's table; everything is fetched one tile ahead (a warp issues in order).
@@ -485,14 +520,14 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
                     b_1 = lds128(zbb + o1.y);
                     if (s + 2 < SLOTS) o2 = lds64u(tw + (s + 2) * 8);
                 }
-                if (s < REG_SLOTS) {
-                    dmma884(acc[s < REG_SLOTS ? s : 0][0], acc[s < REG_SLOTS ? s : 0][1], a_0.x, b_0.x);
-                    dmma884(acc[s < REG_SLOTS ? s : 0][0], acc[s < REG_SLOTS ? s : 0][1], a_0.y, b_0.y);
+                if (s < RS) {
+                    dmma884(acc[s < RS ? s : 0][0], acc[s < RS ? s : 0][1], a_0.x, b_0.x);
+                    dmma884(acc[s < RS ? s : 0][0], acc[s < RS ? s : 0][1], a_0.y, b_0.y);
                 } else {
-                    double2 d = lds128(tm + (s - REG_SLOTS) * 512);
+                    double2 d = lds128(tm + (s - RS) * 512);
                     dmma884(d.x, d.y, a_0.x, b_0.x);
                     dmma884(d.x, d.y, a_0.y, b_0.y);
-                    sts128(tm + (s - REG_SLOTS) * 512, d.x, d.y);
+                    sts128(tm + (s - RS) * 512, d.x, d.y);
                 }
                 a_0 = a_1; b_0 = b_1; o1 = o2;
             }
@@ -597,7 +632,7 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
         srow[i] = s;
     }
     group_sync(gid, gthreads);
-    for (int pb = warp; pb < L; pb += nwarps + 1) {
+    for (int pb = warp; pb < L; pb += (gthreads >> 5)) {
         double s = 0.0;
         for (int i = p.band_start[pb] + lane; i < p.band_start[pb + 1]; i += 32) s += srow[i];
         s = warp_sum(s);
@@ -608,28 +643,30 @@ small_frag_kernel(DevProblem p, EvalBatch b, int T, int Tpad, int gthreads, int 
 
 int padded_T(int T, int nwarps) { return (T + 2 * nwarps - 1) / (2 * nwarps) * (2 * nwarps); }
 
+template <bool HELPER>
 size_t group_smem_doubles(int T, int nwarps, int want_grad) {
+    constexpr int RS = FragCfg<HELPER>::RS;
     const int Np = 8 * T, Tpad = padded_T(T, nwarps);
     const size_t panel = (size_t)4 * Tpad * 64, stage = (size_t)nwarps * 512;
     const size_t part = want_grad ? (size_t)T * T * 8 + (size_t)T * 8 : 0;
-    size_t doubles = (O_TM + (size_t)nwarps * ((SLOTS - REG_SLOTS) * 512 + 512)) / 8 + (panel > stage ? panel : stage) + (size_t)Np * 4 +
-                     (stage + part <= panel ? 0 : part) + (size_t)(Np + 1) / 2 + 2;
+    size_t doubles = (O_TM + (size_t)nwarps * ((SLOTS - RS) * 512 + 512) + (HELPER ? 0 : (size_t)RS * 512)) / 8 + (panel > stage ? panel : stage) +
+                     (size_t)Np * 4 + (stage + part <= panel ? 0 : part) + (size_t)(Np + 1) / 2 + 2;
     return (doubles + 1) & ~(size_t)1;   // keep every group 16-byte aligned
 }
 
-template <int KID>
-cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStream_t s) {
+template <int KID, bool HELPER>
+cudaError_t launch_cfg(const DevProblem& p, const EvalBatch& b, int T, cudaStream_t s) {
     const int ntiles = T * (T + 1) / 2;
     const int nwarps = (ntiles + SLOTS - 1) / SLOTS;
-    const int gthreads = (nwarps + 1) * 32;   // + the helper warp
-    static const int nmat_cap = getenv("GPCC_FRAG_NMAT") ? atoi(getenv("GPCC_FRAG_NMAT")) : 4;
-    const size_t gd = group_smem_doubles(T, nwarps, b.want_grad);
-    const int hwpg = 4 * ((nwarps + 2) / 3);   // hardware warps per matrix: three tile warps per quad + the helper / spare slot
-    int nmat = (MAX_THREADS / 32) / hwpg;
+    const int gthreads = (nwarps + (HELPER ? 1 : 0)) * 32;
+    static const int nmat_cap = getenv("GPCC_FRAG_NMAT") ? atoi(getenv("GPCC_FRAG_NMAT")) : (HELPER ? 4 : 1);
+    const size_t gd = group_smem_doubles<HELPER>(T, nwarps, b.want_grad);
+    const int hwpg = HELPER ? 4 * ((nwarps + 2) / 3) : nwarps;   // hardware warps per matrix (HELPER: three tile warps per quad + the helper / spare slot)
+    int nmat = ((HELPER ? MAX_THREADS : 384) / 32) / hwpg;
     if (nmat > nmat_cap) nmat = nmat_cap;
     while (nmat > 1 && gd * 8 * nmat > 220 * 1024) --nmat;
     if (nmat < 1) nmat = 1;
-    auto kfn = small_frag_kernel<KID>;
+    auto kfn = small_frag_kernel<KID, HELPER>;
     size_t extra = 0;
 #ifdef GPCC_FRAG_PROF
     extra = (size_t)T * 8 * 16 * 8;
@@ -646,6 +683,12 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
                 cudaGetErrorString(rc), hwpg * 32 * nmat, gd * 8 * nmat + extra, fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
     }
     return rc;
+}
+
+template <int KID>
+cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStream_t s) {
+    static const int helper = getenv("GPCC_FRAG_HELPER") ? atoi(getenv("GPCC_FRAG_HELPER")) : 0;
+    return helper ? launch_cfg<KID, true>(p, b, T, s) : launch_cfg<KID, false>(p, b, T, s);
 }
 
 }  // namespace

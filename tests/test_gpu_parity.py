@@ -382,8 +382,9 @@ def test_prior_with_minus_infinity_and_iteration_cap_zero(ctx):
     {"GPCC_SMALL_DMMA": "1"},                                  # small_dmma.cu: rank-8 block sweep, DMMA update, tiles per warp
     {"GPCC_SMALL_BLOCK": "1"},                                 # small_block.cu: blocked DFMA sweep, one matrix per CTA
     {"GPCC_SMALL_BLOCK": "1", "GPCC_BLOCK_VARIANT": "1"},      #                 two matrices per CTA (named barriers)
-    {"GPCC_SMALL_FRAG": "1"},                                  # small_frag.cu: fragment layout, DMMA panel + update, helper warp
-    {"GPCC_SMALL_FRAG": "1", "GPCC_FRAG_NMAT": "1"},
+    {"GPCC_SMALL_FRAG": "1"},                                  # small_frag.cu: fragment layout, DMMA panel + update, 2 CTAs per SM
+    {"GPCC_SMALL_FRAG": "1", "GPCC_FRAG_HELPER": "1"},         #                look-ahead factorisation on a helper warp, 16 warps per SM
+    {"GPCC_SMALL_FRAG": "1", "GPCC_FRAG_HELPER": "1", "GPCC_FRAG_NMAT": "1"},
     {"GPCC_SMALL_VARIANT": "3"},                               # small_sweep.cu with several matrices per CTA
     {"GPCC_SMALL_VARIANT": "4"},                               #                with the straight-line (predicated) step
     {"GPCC_SMALL_VARIANT": "5"},                               #                with two pivots per barrier
