@@ -195,54 +195,86 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
 
     std::vector<LbfgsState> st(m);
     // ---- stage 1: screening of the P start points (:207-209), batched over all candidates -----------
-    // chunked so that one batch never exceeds ~1M evaluations worth of staging
-    const size_t chunk_c = std::max<size_t>(1, std::min<size_t>(m, (size_t)(1 << 18) / std::max(1, P)));
-    int rc = reserve_eval(p, di, chunk_c * P);
-    if (rc) return rc;
     std::vector<double> jac(n);
-    for (size_t c0 = 0; c0 < (size_t)m; c0 += chunk_c) {
-        const size_t c1 = std::min<size_t>(m, c0 + chunk_c);
-        for (size_t c = c0; c < c1; ++c) {
-            const int gi = idx[c];
+    // screening results of the candidates `cand` (evaluations cand-major, P per candidate, in slot q) -> L-BFGS start
+    auto screen_pack = [&](EvalSlot& q, const int* cand, size_t nc) {
+        for (size_t a = 0; a < nc; ++a) {
+            const int gi = idx[cand[a]];
             for (int j = 0; j < P; ++j) {
-                const size_t e = (c - c0) * P + j;
+                const size_t e = a * P + j;
                 const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + j) * n : theta0 + (size_t)j * n;
-                std::memcpy(q0.delays.h + e * L, delays + (size_t)gi * L, L * sizeof(double));
-                unpack_theta(th, L, o, q0.alpha.h + e * L, q0.rho.h + e, nullptr);
+                std::memcpy(q.delays.h + e * L, delays + (size_t)gi * L, L * sizeof(double));
+                unpack_theta(th, L, o, q.alpha.h + e * L, q.rho.h + e, nullptr);
             }
         }
-        rc = evaluate_on_device(p, di, (int)((c1 - c0) * P), 1);
-        if (rc) return rc;
-        for (size_t c = c0; c < c1; ++c) {
-            const int gi = idx[c];
+    };
+    auto screen_feed = [&](EvalSlot& q, const int* cand, size_t nc) {
+        for (size_t a = 0; a < nc; ++a) {
+            const int c = cand[a], gi = idx[c];
             int best = -1;
             double bestf = std::numeric_limits<double>::infinity();
             for (int j = 0; j < P; ++j) {          // argmin of -logL, first minimum wins (Julia argmin, :209)
-                const size_t e = (c - c0) * P + j;
-                const double f = -q0.ll.h[e];
-                if (q0.info.h[e] == 0 && std::isfinite(f) && f < bestf) { bestf = f; best = j; }
+                const size_t e = a * P + j;
+                const double f = -q.ll.h[e];
+                if (q.info.h[e] == 0 && std::isfinite(f) && f < bestf) { bestf = f; best = j; }
             }
             LbfgsState& S = st[c];
             S.n = n;
             S.nfev = P;
             if (best < 0) { S.status = LbfgsState::NO_START; S.f = std::numeric_limits<double>::infinity(); continue; }
-            const size_t e = (c - c0) * P + best;
+            const size_t e = a * P + best;
             const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + best) * n : theta0 + (size_t)best * n;
             double a_[LBFGS_MAXN], r_, g_[LBFGS_MAXN];
             unpack_theta(th, L, o, a_, &r_, jac.data());
-            for (int k = 0; k < n; ++k) g_[k] = -q0.grad.h[e * n + k] * jac[k];
+            for (int k = 0; k < n; ++k) g_[k] = -q.grad.h[e * n + k] * jac[k];
             S.start(n, th, bestf, g_, lo);
+        }
+    };
+    // Fewer active candidates than this: one batch per round instead of two half batches.  Default 2, i.e. the halves
+    // always alternate: with one stream per slot the two small kernels of a latency-bound round overlap on the GPU
+    // (measured: 176-178 ms per fitted cfg3 grid against 179-181 with the threshold at 1024, cfg2 4.3 against 4.6 ms).
+    static const size_t MERGE_BELOW = getenv("GPCC_MERGE_BELOW") ? std::max<size_t>(2, (size_t)atol(getenv("GPCC_MERGE_BELOW"))) : 2;
+    // Fused small-N path with enough candidates: the two halves of stage 2 are formed before the screening, each half is
+    // screened on its own slot / stream, and the first L-BFGS batch of half 0 is packed and launched while the screening of
+    // half 1 still runs (no idle GPU between the stages, host bookkeeping hidden).
+    const bool pipelined = p->small_path && (size_t)m >= MERGE_BELOW && (size_t)m * P <= ((size_t)1 << 18);
+    int rc = 0;
+    std::vector<int> half[2];
+    if (pipelined) {
+        for (int c = 0; c < m; ++c) half[c & 1].push_back(c);
+        rc = reserve_eval(p, di, std::max(half[0].size() * P, (size_t)m), 0);
+        if (rc) return rc;
+        rc = reserve_eval(p, di, half[1].size() * P, 1);
+        if (rc) return rc;
+        for (int g = 0; g < 2; ++g) {
+            screen_pack(s.slot[g], half[g].data(), half[g].size());
+            rc = launch_eval(p, di, g, (int)(half[g].size() * P), 1);
+            if (rc) return rc;
+        }
+    } else {
+        // chunked so that one batch never exceeds ~1M evaluations worth of staging
+        const size_t chunk_c = std::max<size_t>(1, std::min<size_t>(m, (size_t)(1 << 18) / std::max(1, P)));
+        rc = reserve_eval(p, di, chunk_c * P);
+        if (rc) return rc;
+        std::vector<int> seq(m);
+        for (int c = 0; c < m; ++c) seq[c] = c;
+        for (size_t c0 = 0; c0 < (size_t)m; c0 += chunk_c) {
+            const size_t c1 = std::min<size_t>(m, c0 + chunk_c);
+            screen_pack(q0, seq.data() + c0, c1 - c0);
+            rc = evaluate_on_device(p, di, (int)((c1 - c0) * P), 1);
+            if (rc) return rc;
+            screen_feed(q0, seq.data() + c0, c1 - c0);
         }
     }
     // ---- stage 2: batched L-BFGS, software-pipelined over two halves of the candidates -------------------------
     // While the kernel of one half runs, the host feeds the results of the other half to its L-BFGS state machines
     // and packs that half's next trial points (the fused small-N path only; one slot for the tiled path, whose
     // workspace is shared and whose host share is negligible).
-    static const size_t MERGE_BELOW = getenv("GPCC_MERGE_BELOW") ? (size_t)atol(getenv("GPCC_MERGE_BELOW")) : 1024;   // fewer active candidates than this: one batch per round (latency bound)
     int G = (p->small_path && (size_t)m >= MERGE_BELOW) ? 2 : 1;
     std::vector<int> active[2];
-    for (int c = 0; c < m; ++c)
-        if (st[c].status == LbfgsState::RUNNING) active[G == 2 ? (c & 1) : 0].push_back(c);
+    if (!pipelined)
+        for (int c = 0; c < m; ++c)
+            if (st[c].status == LbfgsState::RUNNING) active[G == 2 ? (c & 1) : 0].push_back(c);
     bool launched[2] = {false, false};
     auto pack_and_launch = [&](int g) -> int {
         EvalSlot& q = s.slot[g];
@@ -275,12 +307,23 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
         active[g].resize(w);
         return 0;
     };
-    rc = reserve_eval(p, di, active[0].size() + active[1].size(), 0);
-    if (rc) return rc;
-    rc = reserve_eval(p, di, active[1].size(), 1);
-    if (rc) return rc;
-    for (int g = 0; g < G; ++g)
-        if (!active[g].empty()) { rc = pack_and_launch(g); if (rc) return rc; }
+    if (pipelined) {
+        for (int g = 0; g < 2; ++g) {
+            rc = finish_eval(p, di, g);
+            if (rc) return rc;
+            screen_feed(s.slot[g], half[g].data(), half[g].size());
+            for (int c : half[g])
+                if (st[c].status == LbfgsState::RUNNING) active[g].push_back(c);
+            if (!active[g].empty()) { rc = pack_and_launch(g); if (rc) return rc; }
+        }
+    } else {
+        rc = reserve_eval(p, di, active[0].size() + active[1].size(), 0);
+        if (rc) return rc;
+        rc = reserve_eval(p, di, active[1].size(), 1);
+        if (rc) return rc;
+        for (int g = 0; g < G; ++g)
+            if (!active[g].empty()) { rc = pack_and_launch(g); if (rc) return rc; }
+    }
     while (launched[0] || launched[1]) {
         for (int g = 0; g < G; ++g) {
             if (!launched[g]) continue;
