@@ -7,5 +7,6 @@ reference's README.  All arithmetic on the hot path happens in libgpcc_b200.so (
 marshals arrays.  Julia callers bind the same C ABI through julia/GPCC_B200.jl.
 """
 from .api import (Context, Problem, gpcc, gpccgrid, getprobabilities, uniformpriordelay, Uniform, MvNormal,  # noqa: F401
-                  OU, rbf, matern32, matern52, initial_solutions, default_context, GpccError, performcv, cv_folds)
+                  OU, rbf, matern32, matern52, initial_solutions, default_context, GpccError, performcv, cv_folds,
+                  FitState)
 from .synthetic import simulatetwolightcurves, simulatethreelightcurves, simulatedata, synthetic_bands  # noqa: F401,E402

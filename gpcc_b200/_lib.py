@@ -11,7 +11,8 @@ EXPORTS = [
     "gpcc_ctx_get_stats", "gpcc_ctx_device_count", "gpcc_problem_create", "gpcc_problem_destroy",
     "gpcc_problem_get_prior", "gpcc_loglik_batch", "gpcc_loglik_theta_batch", "gpcc_fit_batch",
     "gpcc_grid_posterior", "gpcc_getprobabilities", "gpcc_postb", "gpcc_predict", "gpcc_predict_loglik",
-    "gpcc_fit_options_default",
+    "gpcc_fit_options_default", "gpcc_fit_state_create", "gpcc_fit_state_destroy", "gpcc_fit_state_postb",
+    "gpcc_fit_state_predict", "gpcc_fit_state_predict_loglik", "gpcc_fit_state_factorisations",
 ]
 
 
@@ -64,9 +65,16 @@ def load():
     lib.gpcc_predict.argtypes = [vp, dp, dp, C.c_double, ip, dp, dp, dp, dp]
     lib.gpcc_predict_loglik.argtypes = [vp, dp, dp, C.c_double, ip, dp, dp, dp, dp, ip]
     lib.gpcc_fit_options_default.argtypes = [C.POINTER(FitOptions)]
+    lib.gpcc_fit_state_create.argtypes = [vp, dp, dp, C.c_double, C.POINTER(vp)]
+    lib.gpcc_fit_state_destroy.argtypes = [vp]
+    lib.gpcc_fit_state_postb.argtypes = [vp, dp, dp]
+    lib.gpcc_fit_state_predict.argtypes = [vp, ip, dp, dp, dp, dp]
+    lib.gpcc_fit_state_predict_loglik.argtypes = [vp, ip, dp, dp, dp, dp, ip]
+    lib.gpcc_fit_state_factorisations.argtypes = [vp]
     for name in EXPORTS:
-        if name not in ("gpcc_last_error",):
+        if name not in ("gpcc_last_error", "gpcc_fit_state_factorisations"):
             getattr(lib, name).restype = C.c_int
+    lib.gpcc_fit_state_factorisations.restype = C.c_longlong
     _lib = lib
     return lib
 

@@ -242,18 +242,26 @@ class Problem:
         return res
 
     # ---- postb (:248-252), predictTest (:259-343) -------------------------------------------------------
+    def fit_state(self, delays, alpha, rho):
+        """The state the reference's `pred` closures capture (:235-252): one factorisation, cached on the device."""
+        return FitState(self, delays, alpha, rho)
+
     def postb(self, delays, alpha, rho):
         delays, alpha = _f64(delays, (self.L,)), _f64(alpha, (self.L,))
         mu, S = np.empty(self.L), np.empty((self.L, self.L))
         check(_lib.load().gpcc_postb(self._h, _d(delays), _d(alpha), float(rho), _d(mu), _d(S)))
         return mu, S
 
-    def predict(self, delays, alpha, rho, ttest_per_band, full_cov=False):
-        delays, alpha = _f64(delays, (self.L,)), _f64(alpha, (self.L,))
+    def _pack_test(self, ttest_per_band):
         nt = np.array([len(a) for a in ttest_per_band], dtype=np.int32)
         if len(nt) != self.L:
             raise GpccError("ttest must have one inner array per band")
         tt = _f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in ttest_per_band])) if nt.sum() else np.empty(0)
+        return nt, tt
+
+    def predict(self, delays, alpha, rho, ttest_per_band, full_cov=False):
+        delays, alpha = _f64(delays, (self.L,)), _f64(alpha, (self.L,))
+        nt, tt = self._pack_test(ttest_per_band)
         NT = int(nt.sum())
         mu, sd = np.empty(NT), np.empty(NT)
         S = np.empty((NT, NT)) if full_cov else None
@@ -262,8 +270,7 @@ class Problem:
 
     def predict_loglik(self, delays, alpha, rho, ttest, ytest, stest):
         delays, alpha = _f64(delays, (self.L,)), _f64(alpha, (self.L,))
-        nt = np.array([len(a) for a in ttest], dtype=np.int32)
-        tt = _f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in ttest]))
+        nt, tt = self._pack_test(ttest)
         yt = _f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in ytest]))
         st = _f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in stest]))
         if not (len(tt) == len(yt) == len(st)):
@@ -272,6 +279,57 @@ class Problem:
         check(_lib.load().gpcc_predict_loglik(self._h, _d(delays), _d(alpha), float(rho), _i(nt), _d(tt), _d(yt), _d(st),
                                               C.byref(ll), C.byref(info)))
         return ll.value, info.value
+
+
+class FitState:
+    """Fitted state of one `gpcc` call on the device (gpcc_fit_state_*): the Cholesky factor of K + Sobs at (delays, alpha, rho),
+    postb, and the scratch of the prediction calls.  The reference's closures capture KSobsB (:241) and re-factorise it on
+    every call (:275, :283); here the N^3 work happens once, in the constructor."""
+
+    def __init__(self, problem, delays, alpha, rho):
+        self.problem = problem              # keeps the problem (and its context) alive
+        self.L = problem.L
+        self.delays, self.alpha, self.rho = _f64(delays, (self.L,)).copy(), _f64(alpha, (self.L,)).copy(), float(rho)
+        self._h = C.c_void_p()
+        check(_lib.load().gpcc_fit_state_create(problem._h, _d(self.delays), _d(self.alpha), self.rho, C.byref(self._h)))
+
+    def postb(self):
+        mu, S = np.empty(self.L), np.empty((self.L, self.L))
+        check(_lib.load().gpcc_fit_state_postb(self._h, _d(mu), _d(S)))
+        return mu, S
+
+    def predict(self, ttest_per_band, full_cov=False):
+        nt, tt = self.problem._pack_test(ttest_per_band)
+        NT = int(nt.sum())
+        mu, sd = np.empty(NT), np.empty(NT)
+        S = np.empty((NT, NT)) if full_cov else None
+        check(_lib.load().gpcc_fit_state_predict(self._h, _i(nt), _d(tt), _d(mu), _d(sd), _d(S)))
+        return mu, sd, S, nt
+
+    def predict_loglik(self, ttest, ytest, stest):
+        nt, tt = self.problem._pack_test(ttest)
+        yt = _f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in ytest]))
+        st = _f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in stest]))
+        if not (len(tt) == len(yt) == len(st)):
+            raise GpccError("test arrays differ in length")
+        ll, info = C.c_double(), C.c_int()
+        check(_lib.load().gpcc_fit_state_predict_loglik(self._h, _i(nt), _d(tt), _d(yt), _d(st), C.byref(ll), C.byref(info)))
+        return ll.value, info.value
+
+    @property
+    def factorisations(self):
+        return int(_lib.load().gpcc_fit_state_factorisations(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.load().gpcc_fit_state_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MvNormal:
@@ -348,28 +406,30 @@ def gpcc(tarray, yarray, stdarray, *, kernel, delays, iterations, seed=1, number
     if verbose:
         out.write("\n\tOverall minimum is %f\n" % (-loglikel))                                          # :228
         out.write("(α, ρ) = unpack(paramopt) = (%s, %s)\n" % (alpha.tolist(), rho))                      # :235
-    mu, S = p.postb(delays, alpha, rho)                                                                  # :248-252
+    state = p.fit_state(delays, alpha, rho)                      # K = delayedCovariance(...); KSobsB (:237-241), factorised once
+    mu, S = state.postb()                                                                                # :248-252
     postb = MvNormal(mu, S)
 
     def pred(ttest, ytest=None, stest=None):                                                             # :259-343
         if ytest is not None:
-            ll, info = p.predict_loglik(delays, alpha, rho, ttest, ytest, stest)
+            ll, info = state.predict_loglik(ttest, ytest, stest)
             if info != 0:
                 # PosDefException branch of the reference (:323-341): nearestposdef(Sigma; minimumeigenvalue=1e-6), i.e.
                 # eigenvalues clamped from below (src/UNUSED/gpcc.jl:294-300 spells it out), then logpdf.  The reference does
                 # this repair in host code (MiscUtil) on an exceptional path; mu and Sigma still come from the device.
-                mu_, _, S_, _ = p.predict(delays, alpha, rho, ttest, full_cov=True)
+                mu_, _, S_, _ = state.predict(ttest, full_cov=True)
                 S_ = S_ + np.diag(np.concatenate([_f64(a) for a in stest]) ** 2)
                 return repaired_logpdf(mu_, S_, np.concatenate([_f64(a) for a in ytest]))
             return ll
         if len(ttest) > 0 and np.ndim(ttest[0]) > 0:                    # Vector{Vector}: (mu, Sigma) (:259-289)
-            mu_, _, S_, _ = p.predict(delays, alpha, rho, ttest, full_cov=True)
+            mu_, _, S_, _ = state.predict(ttest, full_cov=True)
             return mu_, S_
         tt = np.asarray(ttest, dtype=np.float64)                       # Vector: per band (mu, sigma) (:293-307)
-        mu_, sd_, _, _ = p.predict(delays, alpha, rho, [tt] * p.L)
+        mu_, sd_, _, _ = state.predict([tt] * p.L)
         nt = len(tt)
         return [mu_[i * nt:(i + 1) * nt] for i in range(p.L)], [sd_[i * nt:(i + 1) * nt] for i in range(p.L)]
 
+    pred.state = state
     pred.info = dict(nfev=int(res["nfev"][best]), iters=int(res["iters"][best]), status=int(res["info"][best]),
                      theta=res["theta"][best].copy())
     return loglikel, pred, (alpha, postb, rho)

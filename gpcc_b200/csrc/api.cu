@@ -538,7 +538,8 @@ int gpcc_problem_create(gpcc_ctx* ctx, int L, const int* n_per_band, const doubl
     p->pd.resize(ctx->ds.size());
     for (size_t di = 0; di < ctx->ds.size(); ++di) {
         auto& d = p->pd[di];
-        CUDA_TRY(cudaSetDevice(ctx->ds[di].dev));
+        d.dev = ctx->ds[di].dev;
+        CUDA_TRY(cudaSetDevice(d.dev));
         CUDA_TRY(cudaMalloc(&d.t, N * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.resid, N * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.y, N * sizeof(double)));
@@ -561,9 +562,12 @@ int gpcc_problem_create(gpcc_ctx* ctx, int L, const int* n_per_band, const doubl
 
 int gpcc_problem_destroy(gpcc_problem* p) {
     if (!p) return 0;
+    if (p->cached_state) { gpcc_fit_state_destroy(p->cached_state); p->cached_state = nullptr; }
+    // only the problem's own copies of the device ids are read here: the context may already be gone (finalizer order in
+    // Julia / Python is unspecified), see the lifetime rule in include/gpcc_b200.h
     for (size_t di = 0; di < p->pd.size(); ++di) {
-        cudaSetDevice(p->ctx->ds[di].dev);
         auto& d = p->pd[di];
+        cudaSetDevice(d.dev);
         cudaFree(d.t); cudaFree(d.resid); cudaFree(d.y); cudaFree(d.s2); cudaFree(d.sigb); cudaFree(d.band);
     }
     delete p;

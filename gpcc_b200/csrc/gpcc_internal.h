@@ -35,6 +35,8 @@ struct EvalBatch {
     double* dump_kinv = nullptr;     // optional [M][N*N] dense column-major K~^-1 (both triangles)
     double* dump_a = nullptr;        // optional [M][N]   a = K~^-1 (Y - bbar)
     int mode_postb = 0;              // 1: factor Sobs + K WITHOUT B and solve against Y (postb, :248-250)
+    double* dump_chol = nullptr;     // optional [M][N*N] dense column-major Cholesky factor (lower, upper part zero); tiled path,
+                                     // forward mode only (the fitted state behind postb / pred, fitstate.cu)
 };
 
 // ---- small-N path: fused register-resident symmetric sweep (small_sweep.cu) -------------------

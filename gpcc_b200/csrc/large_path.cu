@@ -665,6 +665,18 @@ __global__ void dump_kernel(EvalBatch b, int e0, LargeArgs a) {
         for (int i = threadIdx.x; i < a.N; i += blockDim.x) b.dump_a[(size_t)e * a.N + i] = a.rvec[(size_t)m * a.Np + i];
 }
 
+// dense column-major Cholesky factor (lower triangle, zeros above) out of the tile layout: forward mode only
+__global__ void dump_chol_kernel(EvalBatch b, int e0, LargeArgs a) {
+    const int m = blockIdx.y, e = e0 + m;
+    const double* mat = a.mats + (size_t)m * a.mat_stride;
+    double* out = b.dump_chol + (size_t)e * a.N * a.N;
+    const size_t total = (size_t)a.N * a.N;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(q % a.N), j = (int)(q / a.N);
+        out[q] = i >= j ? mat[tile_index(i >> 7, j >> 7) * TILE_ELEMS + tl_off(i & 127, j & 127)] : 0.0;
+    }
+}
+
 struct LargeImpl {
     int N = 0, T = 0, Np = 0, B = 0;
     size_t mat_stride = 0;
@@ -803,6 +815,10 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, La
     ++launches;
     if (b.dump_kinv) {
         dump_kernel<<<dim3(592, nb), 256, 0, st>>>(b, e0, a);
+        ++launches;
+    }
+    if (b.dump_chol && !a.sweep) {
+        dump_chol_kernel<<<dim3(592, nb), 256, 0, st>>>(b, e0, a);
         ++launches;
     }
     if (profile) cudaEventRecord(w.ev[3], st);

@@ -61,10 +61,11 @@ __device__ __forceinline__ void store8(double* buf, int tile, int T, const doubl
 
 // Publish column `kn` (tile tkn, in-tile index KKN) of the symmetric matrix for the next sweep step.
 // Scalar STS.64 straight from the tile registers (no staging moves); only warps that contain an owner enter.
-template <int KKN>
+template <int KKN, bool FWD = false>
 __device__ __forceinline__ void publish(const double (&A)[8][8], int ti, int tj, int tkn, int kn, int T,
                                         double* nb, double* pslot, double* piv, bool active) {
-    const bool pc = active && (tj == tkn), prw = active && (ti == tkn);
+    // forward-only mode: the row part (tiles left of the pivot tile) is never read again
+    const bool pc = active && (tj == tkn), prw = active && (ti == tkn) && (!FWD || tj == tkn);
     if (!__any_sync(0xffffffffu, pc || prw)) return;
     if (pc) {
         double* dst = nb + 2 * ti;
@@ -85,9 +86,13 @@ __device__ __forceinline__ void publish(const double (&A)[8][8], int ti, int tj,
     }
 }
 
-template <int KK>
+// FWD (forward-only mode, no gradient): plain Gaussian elimination.  Only the tiles with tj >= tk still change something that
+// is read later (the pivots and the border row); the others skip the step, so the work is N^3/3 flop instead of N^3.  The
+// elements that feed the pivots and the corner see exactly the operations of the full sweep: logL is bitwise the same.
+template <int KK, bool FWD>
 __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, int tk, int k, int N, int T, int Np,
                                            double* cbuf, double* pbuf, double* piv, bool active, int gid, int nthreads) {
+    if (FWD && tj < tk) { GROUP_SYNC(); return; }
     const double* cb = cbuf + (k & 1) * VLEN;
     double v[8];
     load8(cb, tj, T, v);
@@ -118,8 +123,8 @@ __device__ __forceinline__ void sweep_step(double (&A)[8][8], int ti, int tj, in
     const int kn = k + 1;
     if (kn < N) {
         double* nb = cbuf + (kn & 1) * VLEN;
-        if (KK < 7) publish<(KK + 1) & 7>(A, ti, tj, tk, kn, T, nb, pbuf + (kn & 1), piv, active);
-        else        publish<0>(A, ti, tj, tk + 1, kn, T, nb, pbuf + (kn & 1), piv, active);
+        if (KK < 7) publish<(KK + 1) & 7, FWD>(A, ti, tj, tk, kn, T, nb, pbuf + (kn & 1), piv, active);
+        else        publish<0, FWD>(A, ti, tj, tk + 1, kn, T, nb, pbuf + (kn & 1), piv, active);
     }
     GROUP_SYNC();
 }
@@ -333,7 +338,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid, int 
     return s;
 }
 
-template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT, bool BF = false, bool PAIR = false>
+template <int KID, int MAXTHREADS, int MINBLOCKS, int NMAT, bool BF = false, bool PAIR = false, bool FWD = false>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
 small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     extern __shared__ __align__(16) double smem_all[];
@@ -348,10 +353,20 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     const int ntiles = T * (T + 1) / 2;
     const bool active = tid < ntiles;
     const int q = active ? tid : ntiles - 1;
-    int ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-    while (ti * (ti + 1) / 2 > q) --ti;
-    while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
-    const int tj = q - ti * (ti + 1) / 2;
+    int ti, tj;
+    if (FWD) {
+        // column-major tile order: the tiles that have left the elimination (tj < tk) are a prefix of the thread range, so
+        // whole warps retire as the pivot moves on instead of every warp keeping a few live lanes
+        int c = 0, rem = q;
+        while (rem >= T - c) { rem -= T - c; ++c; }
+        tj = c;
+        ti = c + rem;
+    } else {
+        ti = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > q) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+        tj = q - ti * (ti + 1) / 2;
+    }
 
     double* tsh = smem;             // shifted times t_i - tau_band(i)         (chunk layout)
     double* av = tsh + VLEN;        // alpha_band(i), 0 for padding            (chunk layout)
@@ -463,14 +478,14 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
     for (int tk = 0; tk < T; ++tk) {
         const int k0 = tk * 8;
         if (k0 >= N) break;
-        sweep_step<0>(A, ti, tj, tk, k0 + 0, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 1 >= N) break;
-        sweep_step<1>(A, ti, tj, tk, k0 + 1, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 2 >= N) break;
-        sweep_step<2>(A, ti, tj, tk, k0 + 2, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 3 >= N) break;
-        sweep_step<3>(A, ti, tj, tk, k0 + 3, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 4 >= N) break;
-        sweep_step<4>(A, ti, tj, tk, k0 + 4, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 5 >= N) break;
-        sweep_step<5>(A, ti, tj, tk, k0 + 5, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 6 >= N) break;
-        sweep_step<6>(A, ti, tj, tk, k0 + 6, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 7 >= N) break;
-        sweep_step<7>(A, ti, tj, tk, k0 + 7, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads);
+        sweep_step<0, FWD>(A, ti, tj, tk, k0 + 0, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 1 >= N) break;
+        sweep_step<1, FWD>(A, ti, tj, tk, k0 + 1, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 2 >= N) break;
+        sweep_step<2, FWD>(A, ti, tj, tk, k0 + 2, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 3 >= N) break;
+        sweep_step<3, FWD>(A, ti, tj, tk, k0 + 3, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 4 >= N) break;
+        sweep_step<4, FWD>(A, ti, tj, tk, k0 + 4, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 5 >= N) break;
+        sweep_step<5, FWD>(A, ti, tj, tk, k0 + 5, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 6 >= N) break;
+        sweep_step<6, FWD>(A, ti, tj, tk, k0 + 6, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads); if (k0 + 7 >= N) break;
+        sweep_step<7, FWD>(A, ti, tj, tk, k0 + 7, N, T, Np, cbuf, pbuf, piv, active, gid, nthreads);
     }
     }
 
@@ -502,7 +517,7 @@ small_sweep_kernel(DevProblem p, EvalBatch b, int T, int group_doubles) {
         b.ll[e] = info ? -INFINITY : ll;
         if (b.info) b.info[e] = info;
     }
-    if (!b.want_grad) return;
+    if (FWD || !b.want_grad) return;
     if (info) {
         if (tid <= L) b.grad[(size_t)e * (L + 1) + tid] = 0.0;
         return;
@@ -614,12 +629,21 @@ size_t smem_bytes(int T, int want_grad) {
     return doubles * sizeof(double) + (size_t)Np * sizeof(int) + 16;
 }
 
+template <int KID, int MT, int MB, int NMAT, bool BF, bool PAIR, bool FWD>
+void go(const DevProblem& p, const EvalBatch& b, int T, int gd, int threads, int maxT, cudaStream_t s) {
+    auto kfn = small_sweep_kernel<KID, MT, MB, NMAT, BF, PAIR, FWD>;
+    const size_t group_bytes = (size_t)gd * 8;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, NMAT * 8 * (int)((smem_bytes(maxT, 1) + 15) / 16 * 2));
+    kfn<<<(b.M + NMAT - 1) / NMAT, NMAT * threads, NMAT * group_bytes, s>>>(p, b, T, gd);
+}
+
 template <int KID>
 cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStream_t s) {
     const int ntiles = T * (T + 1) / 2;
     const int threads = (ntiles + 31) / 32 * 32;
     const size_t sm = smem_bytes(T, b.want_grad);
     static const int variant_env = getenv("GPCC_SMALL_VARIANT") ? atoi(getenv("GPCC_SMALL_VARIANT")) : -1;
+    static const bool no_fwd = getenv("GPCC_SMALL_NO_FWD") != nullptr;
     static int nsm = 0;
     if (nsm == 0) {
         int dev = 0;
@@ -634,44 +658,35 @@ cudaError_t launch_kid(const DevProblem& p, const EvalBatch& b, int T, cudaStrea
     int variant = variant_env;
     if (variant < 0) variant = (threads <= 128) ? (b.M >= 3 * nsm ? 2 : 1) : (b.M <= nsm ? 0 : 1);
     const int gd = (int)((sm + 15) / 16 * 2);   // doubles per group, 16-byte aligned
+    // forward-only mode (N^3/3 flop): no gradient and nothing that needs the inverse or a = K~^-1 r
+    const bool fwd = !no_fwd && !b.want_grad && !b.dump_kinv && !b.dump_a && variant_env < 0;
+    if (fwd) {
+        if (threads <= 128) {
+            if (variant == 2) go<KID, 128, 3, 1, false, false, true>(p, b, T, gd, threads, 15, s);
+            else              go<KID, 128, 2, 1, false, false, true>(p, b, T, gd, threads, 15, s);
+        } else if (threads <= 192) go<KID, 192, 2, 1, false, false, true>(p, b, T, gd, threads, 19, s);
+        else if (threads <= 224)   go<KID, 224, 1, 1, false, false, true>(p, b, T, gd, threads, 20, s);
+        else                       go<KID, 352, 1, 1, false, false, true>(p, b, T, gd, threads, SMALL_MAX_T, s);
+        return cudaGetLastError();
+    }
     if (threads <= 128) {
-        if (variant == 3) {   // three matrices per CTA: 12 warps, 3 per scheduler
-            auto kfn = small_sweep_kernel<KID, 384, 1, 3>;
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * (int)((smem_bytes(15, 1) + 15) / 16 * 2));
-            kfn<<<(b.M + 2) / 3, 3 * threads, (size_t)3 * gd * 8, s>>>(p, b, T, gd);
-        } else if (variant == 2) {
-            auto kfn = small_sweep_kernel<KID, 128, 3, 1>;
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
-            kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
-        } else {
-            auto kfn = small_sweep_kernel<KID, 128, 2, 1>;
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(15, 1));
-            kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
-        }
+        if (variant == 3)      go<KID, 384, 1, 3, false, false, false>(p, b, T, gd, threads, 15, s);   // three matrices per CTA: 12 warps, 3 per scheduler
+        else if (variant == 2) go<KID, 128, 3, 1, false, false, false>(p, b, T, gd, threads, 15, s);
+        else                   go<KID, 128, 2, 1, false, false, false>(p, b, T, gd, threads, 15, s);
     } else if (threads <= 192 && variant == 3) {   // two matrices per CTA: 12 warps, 3 per scheduler
-        auto kfn = small_sweep_kernel<KID, 384, 1, 2>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (int)((smem_bytes(19, 1) + 15) / 16 * 2));
-        kfn<<<(b.M + 1) / 2, 2 * threads, (size_t)2 * gd * 8, s>>>(p, b, T, gd);
+        go<KID, 384, 1, 2, false, false, false>(p, b, T, gd, threads, 19, s);
     } else if (threads <= 192 && variant == 5 && (p.N % 2) == 0) {   // two pivots per barrier
-        auto kfn = small_sweep_kernel<KID, 192, 2, 1, false, true>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
+        go<KID, 192, 2, 1, false, true, false>(p, b, T, gd, threads, 19, s);
+    } else if (threads <= 192 && variant == 6 && (p.N % 2) == 0) {   // two pivots per barrier, one CTA per SM at 255 registers (no spills)
+        go<KID, 192, 1, 1, false, true, false>(p, b, T, gd, threads, 19, s);
     } else if (threads <= 192 && variant == 4) {   // branch-free step
-        auto kfn = small_sweep_kernel<KID, 192, 2, 1, true>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
+        go<KID, 192, 2, 1, true, false, false>(p, b, T, gd, threads, 19, s);
     } else if (threads <= 192 && variant == 1) {
-        auto kfn = small_sweep_kernel<KID, 192, 2, 1>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(19, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
+        go<KID, 192, 2, 1, false, false, false>(p, b, T, gd, threads, 19, s);
     } else if (threads <= 224) {
-        auto kfn = small_sweep_kernel<KID, 224, 1, 1>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(20, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
+        go<KID, 224, 1, 1, false, false, false>(p, b, T, gd, threads, 20, s);
     } else {
-        auto kfn = small_sweep_kernel<KID, 352, 1, 1>;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(SMALL_MAX_T, 1));
-        kfn<<<b.M, threads, sm, s>>>(p, b, T, gd);
+        go<KID, 352, 1, 1, false, false, false>(p, b, T, gd, threads, SMALL_MAX_T, s);
     }
     return cudaGetLastError();
 }

@@ -81,18 +81,22 @@ struct gpcc_ctx {
     gpcc::NcclBridge* nccl = nullptr;
 };
 
+struct gpcc_fit_state;
+
 struct gpcc_problem {
     gpcc_ctx* ctx = nullptr;
     int L = 0, N = 0, kernel_id = 0;
     std::vector<int> n_per_band, band, band_start;
     std::vector<double> t, y, sigma, mub, Sigmab, resid, s2, sigb;
     struct PerDev {
+        int dev = 0;              // CUDA device id, copied from the context at creation: destroying a problem never reads the context
         double *t = nullptr, *resid = nullptr, *y = nullptr, *s2 = nullptr, *sigb = nullptr;
         int* band = nullptr;
         gpcc::DevProblem dp;
     };
     std::vector<PerDev> pd;
     bool small_path = true;
+    gpcc_fit_state* cached_state = nullptr;   // fitted state of the last gpcc_postb / gpcc_predict* call (predict.cu)
 };
 
 namespace gpcc {

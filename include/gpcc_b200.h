@@ -15,6 +15,9 @@
  *     never a return code.  No exception, exit or signal crosses the boundary.
  *   - calls are synchronous; a context is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device gpcc_ctx_create fails.
+ *   - lifetime: a problem and a fit state may only be USED while their context (and, for a fit state, its problem)
+ *     is alive; they may be DESTROYED in any order, also after the context (garbage-collected hosts run
+ *     finalizers in unspecified order): destroy functions only touch memory the object itself owns.
  */
 #ifndef GPCC_B200_H
 #define GPCC_B200_H
@@ -34,6 +37,7 @@ enum { GPCC_TRANSFORM_SOFTPLUS_LOGISTIC = 0 };
 
 typedef struct gpcc_ctx gpcc_ctx;
 typedef struct gpcc_problem gpcc_problem;
+typedef struct gpcc_fit_state gpcc_fit_state;
 
 /* Keyword arguments / constants of gpcc (src/gpccfixdelay_marginaliseb.jl:46, :69, :112, :205). */
 typedef struct gpcc_fit_options {
@@ -122,7 +126,26 @@ int gpcc_grid_posterior(gpcc_problem* p, int M, const double* delays, const doub
  * logprior NULL = the 1-argument method (:1-6).                                                     */
 int gpcc_getprobabilities(gpcc_ctx* ctx, int M, const double* loglik, const double* logprior, double* out_post);
 
-/* Posterior of the shifts b (src/gpccfixdelay_marginaliseb.jl:248-252): out_mu[L], out_Sigma[L*L].  */
+/* What the reference's `pred` closures capture after the fit (src/gpccfixdelay_marginaliseb.jl:235-252: alpha, rho,
+ * KSobsB, postb): ONE Cholesky factorisation of K + Sobs at the fitted (delays, alpha, rho), kept on the device
+ * together with postb, and reused by every later prediction (the reference re-factorises on each call, :275, :283).
+ * Returns -6 when K + Sobs is not positive definite.                                                   */
+int gpcc_fit_state_create(gpcc_problem* p, const double* delays, const double* alpha, double rho, gpcc_fit_state** out);
+int gpcc_fit_state_destroy(gpcc_fit_state* s);
+/* postb (:248-252): out_mu[L], out_Sigma[L*L] (symmetrised, :252).                                     */
+int gpcc_fit_state_postb(const gpcc_fit_state* s, double* out_mu, double* out_Sigma);
+/* predictTest (:259-307) and the test log-likelihood (:311-343) from the cached factor; arguments as in
+ * gpcc_predict / gpcc_predict_loglik below.                                                            */
+int gpcc_fit_state_predict(gpcc_fit_state* s, const int* ntest_per_band, const double* ttest, double* out_mu,
+                           double* out_sd, double* out_Sigma);
+int gpcc_fit_state_predict_loglik(gpcc_fit_state* s, const int* ntest_per_band, const double* ttest,
+                                  const double* ytest, const double* sigmatest, double* out_ll, int* out_info);
+/* diagnostics: number of N^3 factorisations this state has run (1 for its whole life).               */
+long long gpcc_fit_state_factorisations(const gpcc_fit_state* s);
+
+/* Stateless forms of the three calls above.  They keep the fit state of the most recent (delays, alpha, rho) on
+ * the problem, so postb + any number of pred calls at the fitted hyper-parameters share one factorisation.
+ * Posterior of the shifts b (src/gpccfixdelay_marginaliseb.jl:248-252): out_mu[L], out_Sigma[L*L].  */
 int gpcc_postb(gpcc_problem* p, const double* delays, const double* alpha, double rho, double* out_mu,
                double* out_Sigma);
 

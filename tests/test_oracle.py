@@ -195,3 +195,54 @@ def test_posterior_mode_near_true_delays_3band():
     g = load_golden("fit_cfg3_subgrid")
     assert np.allclose(g["delays"][np.argmax(g["post"])], [0.0, 2.0, 4.0])
     assert g["post"].sum() == pytest.approx(1.0)
+
+
+# ---- postb / pred against 50-digit arithmetic (tests/golden/pred_exact.npz, oracle/exact.py) ---------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_pred_and_postb_against_exact_fixture(tag):
+    """The float64 oracle follows the reference's route (LU solves with KSobsB, :275-285; two solves with K+Sobs, :248-250);
+    sigma_pred cancels ~4 digits there, so it is held to 1e-9 against the 50-digit values, one decade inside the 1e-8 the
+    device library is held to against the same fixture."""
+    g = load_golden("pred_exact")
+    idx = np.cumsum(g[tag + "_n"])[:-1]
+    t, y, s = np.split(g[tag + "_t"], idx), np.split(g[tag + "_y"], idx), np.split(g[tag + "_s"], idx)
+    tt = np.split(g[tag + "_ttest"], np.cumsum(g[tag + "_ntest"])[:-1])
+    p = oracle.Problem(t, y, s, str(g[tag + "_kernel"]))
+    d, a, r = g[tag + "_delays"], g[tag + "_alpha"], float(g[tag + "_rho"])
+    mu_b, S_b = p.postb(d, a, r)
+    assert np.allclose(mu_b, g[tag + "_postb_mu"], rtol=1e-10) and np.allclose(S_b, g[tag + "_postb_Sigma"], rtol=1e-9)
+    mu, S = p.predict_full(d, a, r, tt)
+    sd = np.sqrt(np.maximum(np.diag(S), 1e-6))
+    assert np.max(np.abs(mu - g[tag + "_pred_mu"]) / np.abs(g[tag + "_pred_mu"])) < 1e-10
+    assert np.max(np.abs(sd - g[tag + "_pred_sd"]) / g[tag + "_pred_sd"]) < 1e-9
+    assert np.max(np.abs(S - g[tag + "_pred_Sigma"])) / np.max(np.abs(g[tag + "_pred_Sigma"])) < 1e-9
+
+
+def test_exact_module_reproduces_fixture_on_a_small_case():
+    """oracle/exact.py itself (mpmath, 50 digits) on a 12-point problem: agrees with the float64 oracle to rounding, and its
+    postb agrees with Gaussian conditioning on the B-inflated covariance (an independent route)."""
+    from oracle.exact import postb_exact, predict_exact
+    t, y, s, d = oracle.synthetic_bands([7, 5], seed=2, span=8.0)
+    p = oracle.Problem(t, y, s, "matern32")
+    alpha, rho = np.array([1.2, 0.7]), 2.5
+    mu_b, S_b = postb_exact(p, d, alpha, rho)
+    Kt = p.Ktilde(d, alpha, rho)
+    Q = (p.band[:, None] == np.arange(2)[None, :]).astype(float)
+    Sb = np.diag(p.Sigmab)
+    cond_mu = p.mub + Sb @ Q.T @ np.linalg.solve(Kt, p.Y - p.bbar)
+    cond_S = Sb - Sb @ Q.T @ np.linalg.solve(Kt, Q @ Sb)
+    assert np.allclose(mu_b, cond_mu, rtol=1e-9) and np.allclose(S_b, cond_S, rtol=1e-6)
+    tt = [np.array([1.0, 4.0]), np.array([2.0])]
+    mu, S, sd = predict_exact(p, d, alpha, rho, tt)
+    om, oS = p.predict_full(d, alpha, rho, tt)
+    assert np.allclose(mu, om, rtol=1e-11) and np.allclose(S, oS, rtol=1e-9, atol=1e-12)
+
+
+def test_full_cfg3_fixture_is_self_consistent():
+    g = load_golden("fit_cfg3_full")
+    assert g["ll"].shape == (10201,) and abs(g["post"].sum() - 1.0) < 1e-12
+    sub = load_golden("fit_cfg3_subgrid")
+    # the 121-candidate sub-grid fixture is a subset of the full grid: same optimiser, same values
+    for dl, ll in zip(sub["delays"][::7], sub["ll"][::7]):
+        k = int(np.argmin(np.abs(g["delays"] - dl).sum(axis=1)))
+        assert np.allclose(g["delays"][k], dl) and abs(g["ll"][k] - ll) < 1e-9
