@@ -97,6 +97,13 @@ class Context:
     def set_profiling(self, on):
         check(_lib.load().gpcc_ctx_set_profiling(self._h, 1 if on else 0))
 
+    def comm_init_rank(self, world, rank, unique_id):
+        """Join a multi-process communicator (one process per GPU): see gpcc_ctx_comm_init_rank."""
+        if len(unique_id) != 128:
+            raise GpccError("the NCCL unique id is 128 bytes")
+        check(_lib.load().gpcc_ctx_comm_init_rank(self._h, int(world), int(rank), bytes(unique_id)))
+        self.world, self.rank = int(world), int(rank)
+
     @property
     def ndev(self):
         return _lib.load().gpcc_ctx_device_count(self._h)
@@ -123,6 +130,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def comm_unique_id():
+    """128-byte NCCL id drawn by rank 0; broadcast it to the other ranks with whatever the host program uses."""
+    buf = C.create_string_buffer(128)
+    check(_lib.load().gpcc_comm_unique_id(buf))
+    return buf.raw
 
 
 _default_ctx = None

@@ -13,6 +13,7 @@
 #include <limits>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 using namespace gpcc;
@@ -53,8 +54,7 @@ int check_options(const gpcc_fit_options* o) {
 // Evaluate `M` (delay, alpha, rho) triples that already sit in the pinned host mirrors of `s`.
 // Results land in s.ll.h / s.grad.h / s.info.h.
 }  // namespace
-int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, double* dump_kinv, double* dump_a,
-                      int mode_postb) {
+int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad) {
     DeviceState& s = p->ctx->ds[di];
     EvalSlot& q = s.slot[slot];
     const int L = p->L;
@@ -66,18 +66,12 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, d
     CUDA_TRY(cudaMemcpyAsync(q.rho.d, q.rho.h, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, stream));
     EvalBatch b;
     b.M = M; b.delays = q.delays.d; b.alpha = q.alpha.d; b.rho = q.rho.d; b.want_grad = want_grad;
-    b.ll = q.ll.d; b.grad = q.grad.d; b.info = q.info.d; b.dump_kinv = dump_kinv; b.dump_a = dump_a; b.mode_postb = mode_postb;
+    b.ll = q.ll.d; b.grad = q.grad.d; b.info = q.info.d;
     const bool prof = p->ctx->profiling;
     q.M = M; q.want_grad = want_grad; q.timed = false;
     if (p->small_path) {
         if (prof) CUDA_TRY(cudaEventRecord(q.ev0, stream));
-        static const int use_dmma = getenv("GPCC_SMALL_DMMA") ? atoi(getenv("GPCC_SMALL_DMMA")) : 0;
-        static const int use_block = getenv("GPCC_SMALL_BLOCK") ? atoi(getenv("GPCC_SMALL_BLOCK")) : 0;
-        static const int use_frag = getenv("GPCC_SMALL_FRAG") ? atoi(getenv("GPCC_SMALL_FRAG")) : 0;
-        if (use_frag && small_frag_supports(p->N)) CUDA_TRY(small_frag_launch(p->pd[di].dp, b, stream));
-        else if (use_block && small_block_supports(p->N)) CUDA_TRY(small_block_launch(p->pd[di].dp, b, stream));
-        else if (use_dmma && small_dmma_supports(p->N)) CUDA_TRY(small_dmma_launch(p->pd[di].dp, b, stream));
-        else CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, stream));
+        CUDA_TRY(small_sweep_launch(p->pd[di].dp, b, stream));
         if (prof) CUDA_TRY(cudaEventRecord(q.ev1, stream));
         q.timed = prof;
         s.launches += 1;
@@ -115,9 +109,8 @@ int gpcc::finish_eval(gpcc_problem* p, int di, int slot) {
     return 0;
 }
 
-int gpcc::evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv, double* dump_a,
-                             int mode_postb) {
-    int rc = launch_eval(p, di, 0, M, want_grad, dump_kinv, dump_a, mode_postb);
+int gpcc::evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad) {
+    int rc = launch_eval(p, di, 0, M, want_grad);
     if (rc) return rc;
     return finish_eval(p, di, 0);
 }
@@ -180,12 +173,123 @@ struct FitOutputs {
     int *iters, *nfev, *info;
 };
 
+void write_fit_outputs(const gpcc_problem* p, const gpcc_fit_options& o, const FitOutputs& out, int gi, double f, const double* x,
+                       int iters, int nfev, int status) {
+    const int L = p->L, n = L + 1;
+    if (out.ll) out.ll[gi] = -f;                                           // -result.minimum (:351)
+    if (out.iters) out.iters[gi] = iters;
+    if (out.nfev) out.nfev[gi] = nfev;
+    if (out.info) out.info[gi] = status;
+    double a_[LBFGS_MAXN], r_ = std::numeric_limits<double>::quiet_NaN();
+    if (status == LbfgsState::NO_START) {
+        for (int k = 0; k < L; ++k) a_[k] = std::numeric_limits<double>::quiet_NaN();
+        if (out.theta) for (int k = 0; k < n; ++k) out.theta[(size_t)gi * n + k] = std::numeric_limits<double>::quiet_NaN();
+    } else {
+        unpack_theta(x, L, o, a_, &r_, nullptr);                            // unpack(paramopt) (:235)
+        if (out.theta) std::memcpy(out.theta + (size_t)gi * n, x, n * sizeof(double));
+    }
+    if (out.alpha) std::memcpy(out.alpha + (size_t)gi * L, a_, L * sizeof(double));
+    if (out.rho) out.rho[gi] = r_;
+}
+
+// Fused small-N path: the whole shard in ONE launch of the persistent fit kernel (small_fit.cu) -- screening, L-BFGS and
+// every likelihood / gradient evaluation stay on the device; the host uploads delays + start points and reads the optima.
+int fit_shard_device(gpcc_problem* p, int di, const std::vector<int>& idx, const double* delays, int P, const double* theta0,
+                     const gpcc_fit_options& o, const FitOutputs& out) {
+    const int L = p->L, n = L + 1;
+    const int m = (int)idx.size();
+    DeviceState& s = p->ctx->ds[di];
+    CUDA_TRY(cudaSetDevice(s.dev));
+    const size_t nth = (size_t)(o.theta0_per_candidate ? m : 1) * P * n;
+    CUDA_TRY(s.fit_delays.reserve((size_t)m * L));
+    CUDA_TRY(s.fit_theta0.reserve(nth));
+    CUDA_TRY(s.fit_ll.reserve(m));
+    CUDA_TRY(s.fit_theta.reserve((size_t)m * n));
+    CUDA_TRY(s.fit_iters.reserve(m));
+    CUDA_TRY(s.fit_nfev.reserve(m));
+    CUDA_TRY(s.fit_status.reserve(m));
+    CUDA_TRY(s.fit_counters.reserve(8));
+    CUDA_TRY(s.fit_order.reserve(m));
+    for (int c = 0; c < m; ++c) std::memcpy(s.fit_delays.h + (size_t)c * L, delays + (size_t)idx[c] * L, L * sizeof(double));
+    if (o.theta0_per_candidate)
+        for (int c = 0; c < m; ++c) std::memcpy(s.fit_theta0.h + (size_t)c * P * n, theta0 + (size_t)idx[c] * P * n, (size_t)P * n * sizeof(double));
+    else
+        std::memcpy(s.fit_theta0.h, theta0, (size_t)P * n * sizeof(double));
+    // Work-queue order.  A persistent CTA runs its candidate to convergence, so the launch ends when the last-started long
+    // candidate ends: candidates that are likely to need many iterations should start first.  Evaluation counts are hardly
+    // predictable (measured: correlation 0.2 with the screening likelihood or with the neighbours on the grid), except that
+    // the flattest likelihoods -- and with them the longest L-BFGS runs -- sit where the light curves overlap least, i.e. at
+    // the largest spread of delays (profiles/README.md, scheduling study: grid order 13 % over the ideal span, this 5 %).
+    // The order cannot change any result: candidates never interact.
+    {
+        std::vector<std::pair<double, int>> key(m);
+        for (int c = 0; c < m; ++c) {
+            const double* dl = delays + (size_t)idx[c] * L;
+            double lo = dl[0], hi = dl[0];
+            for (int l = 1; l < L; ++l) { lo = std::min(lo, dl[l]); hi = std::max(hi, dl[l]); }
+            key[c] = {-(hi - lo), c};
+        }
+        static const bool grid_order = getenv("GPCC_FIT_GRID_ORDER") != nullptr;      // A/B switch
+        if (!grid_order) std::stable_sort(key.begin(), key.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+        for (int c = 0; c < m; ++c) s.fit_order.h[c] = key[c].second;
+    }
+    for (int k = 0; k < 8; ++k) s.fit_counters.h[k] = 0;
+    s.fit_counters.h[5] = ~0ULL;
+    cudaStream_t st = s.stream;
+    CUDA_TRY(cudaMemcpyAsync(s.fit_delays.d, s.fit_delays.h, (size_t)m * L * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_theta0.d, s.fit_theta0.h, nth * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_counters.d, s.fit_counters.h, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_order.d, s.fit_order.h, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+    FitParams fp;
+    fp.M = m; fp.P = P; fp.theta0_per_candidate = o.theta0_per_candidate; fp.max_iter = o.max_iter;
+    fp.rhomin = o.rhomin; fp.rhomax = o.rhomax; fp.alpha_floor = o.alpha_floor; fp.gtol = o.gtol; fp.ftol = o.ftol;
+    fp.history = o.history;
+    static const bool screen_full = getenv("GPCC_SCREEN_FULL") != nullptr;     // experiment switch: screen with gradient evaluations
+    fp.screen_forward = screen_full ? 0 : 1;
+    FitBuffers fb;
+    fb.delays = s.fit_delays.d; fb.theta0 = s.fit_theta0.d; fb.ll = s.fit_ll.d; fb.theta = s.fit_theta.d;
+    fb.iters = s.fit_iters.d; fb.nfev = s.fit_nfev.d; fb.status = s.fit_status.d; fb.counters = s.fit_counters.d;
+    fb.order = s.fit_order.d;
+    const bool prof = p->ctx->profiling;
+    if (prof) CUDA_TRY(cudaEventRecord(s.fit_ev0, st));
+    CUDA_TRY(small_fit_launch(p->pd[di].dp, fp, fb, st));
+    if (prof) CUDA_TRY(cudaEventRecord(s.fit_ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_ll.h, s.fit_ll.d, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_theta.h, s.fit_theta.d, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_iters.h, s.fit_iters.d, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_nfev.h, s.fit_nfev.d, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_status.h, s.fit_status.d, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s.fit_counters.h, s.fit_counters.d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (prof) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s.fit_ev0, s.fit_ev1));
+        s.ms_eval += ms;
+    }
+    static const bool debug = getenv("GPCC_FIT_DEBUG") != nullptr;
+    if (debug && s.fit_counters.h[6] > 0) {
+        const double span = (double)(s.fit_counters.h[4] - s.fit_counters.h[5]) * 1e-6;
+        const double mean_exit = (double)s.fit_counters.h[3] / (double)s.fit_counters.h[6] * 1e-6;
+        fprintf(stderr, "[gpcc fit] %d candidates on %llu CTAs: kernel span %.2f ms, mean CTA exit at %.2f ms (%.1f %% of the CTA-time busy), "
+                        "%llu gradient + %llu forward evaluations\n", m, s.fit_counters.h[6], span, mean_exit, 100.0 * mean_exit / span,
+                s.fit_counters.h[1], s.fit_counters.h[2]);
+    }
+    s.launches += 1;
+    s.evals += (long long)(s.fit_counters.h[1] + s.fit_counters.h[2]);
+    s.evals_grad += (long long)s.fit_counters.h[1];
+    for (int c = 0; c < m; ++c)
+        write_fit_outputs(p, o, out, idx[c], -s.fit_ll.h[c], s.fit_theta.h + (size_t)c * n, s.fit_iters.h[c], s.fit_nfev.h[c], s.fit_status.h[c]);
+    return 0;
+}
+
 // Candidates idx[0..n) (global indices) are fitted on device `di`.
 int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double* delays, int P, const double* theta0,
               const gpcc_fit_options& o, const FitOutputs& out) {
     const int L = p->L, n = L + 1;
     const int m = (int)idx.size();
     if (m == 0) return 0;
+    static const bool host_loop = getenv("GPCC_FIT_HOST") != nullptr;          // A/B switch: host-driven batched L-BFGS on the small path
+    if (p->small_path && !host_loop) return fit_shard_device(p, di, idx, delays, P, theta0, o, out);
     DeviceState& s = p->ctx->ds[di];
     EvalSlot& q0 = s.slot[0];
     LbfgsOptions lo;
@@ -224,6 +328,11 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
             if (best < 0) { S.status = LbfgsState::NO_START; S.f = std::numeric_limits<double>::infinity(); continue; }
             const size_t e = a * P + best;
             const double* th = o.theta0_per_candidate ? theta0 + ((size_t)gi * P + best) * n : theta0 + (size_t)best * n;
+            if (o.max_iter <= 0) {           // screening only (:207-209): the evaluations ran without gradient
+                lb_copy(S.x, th, n);
+                S.f = bestf; S.iters = 0; S.status = LbfgsState::ITER_CAP;
+                continue;
+            }
             double a_[LBFGS_MAXN], r_, g_[LBFGS_MAXN];
             unpack_theta(th, L, o, a_, &r_, jac.data());
             for (int k = 0; k < n; ++k) g_[k] = -q.grad.h[e * n + k] * jac[k];
@@ -239,6 +348,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
     // half 1 still runs (no idle GPU between the stages, host bookkeeping hidden).
     const bool pipelined = p->small_path && (size_t)m >= MERGE_BELOW && (size_t)m * P <= ((size_t)1 << 18);
     int rc = 0;
+    const int screen_grad = o.max_iter > 0 ? 1 : 0;      // iterations = 0: the fixed-theta sweep, forward-only evaluations
     std::vector<int> half[2];
     if (pipelined) {
         for (int c = 0; c < m; ++c) half[c & 1].push_back(c);
@@ -248,7 +358,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
         if (rc) return rc;
         for (int g = 0; g < 2; ++g) {
             screen_pack(s.slot[g], half[g].data(), half[g].size());
-            rc = launch_eval(p, di, g, (int)(half[g].size() * P), 1);
+            rc = launch_eval(p, di, g, (int)(half[g].size() * P), screen_grad);
             if (rc) return rc;
         }
     } else {
@@ -261,7 +371,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
         for (size_t c0 = 0; c0 < (size_t)m; c0 += chunk_c) {
             const size_t c1 = std::min<size_t>(m, c0 + chunk_c);
             screen_pack(q0, seq.data() + c0, c1 - c0);
-            rc = evaluate_on_device(p, di, (int)((c1 - c0) * P), 1);
+            rc = evaluate_on_device(p, di, (int)((c1 - c0) * P), screen_grad);
             if (rc) return rc;
             screen_feed(q0, seq.data() + c0, c1 - c0);
         }
@@ -342,24 +452,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
         }
     }
     // ---- outputs ------------------------------------------------------------------------------------------
-    for (int c = 0; c < m; ++c) {
-        const int gi = idx[c];
-        const LbfgsState& S = st[c];
-        if (out.ll) out.ll[gi] = -S.f;                                         // -result.minimum (:351)
-        if (out.iters) out.iters[gi] = S.iters;
-        if (out.nfev) out.nfev[gi] = S.nfev;
-        if (out.info) out.info[gi] = S.status;
-        double a_[LBFGS_MAXN], r_ = std::numeric_limits<double>::quiet_NaN();
-        if (S.status == LbfgsState::NO_START) {
-            for (int k = 0; k < L; ++k) a_[k] = std::numeric_limits<double>::quiet_NaN();
-            if (out.theta) for (int k = 0; k < n; ++k) out.theta[(size_t)gi * n + k] = std::numeric_limits<double>::quiet_NaN();
-        } else {
-            unpack_theta(S.x, L, o, a_, &r_, nullptr);                          // unpack(paramopt) (:235)
-            if (out.theta) std::memcpy(out.theta + (size_t)gi * n, S.x, n * sizeof(double));
-        }
-        if (out.alpha) std::memcpy(out.alpha + (size_t)gi * L, a_, L * sizeof(double));
-        if (out.rho) out.rho[gi] = r_;
-    }
+    for (int c = 0; c < m; ++c) write_fit_outputs(p, o, out, idx[c], st[c].f, st[c].x, st[c].iters, st[c].nfev, st[c].status);
     return 0;
 }
 
@@ -384,7 +477,12 @@ int fit_all(gpcc_problem* p, int M, const double* delays, int P, const double* t
     gpcc_ctx* ctx = p->ctx;
     const int nd = (int)ctx->ds.size();
     std::vector<std::vector<int>> shard(nd);
-    for (int m = 0; m < M; ++m) shard[m % nd].push_back(m);     // candidate m -> device m mod ndev
+    // candidate m -> global device m mod G, G = ranks x devices per rank; this process owns G-indices rank*nd + di
+    const int G = ctx->world * nd;
+    for (int m = 0; m < M; ++m) {
+        const int g = m % G;
+        if (g / nd == ctx->rank) shard[g % nd].push_back(m);
+    }
     return for_each_device(ctx, [&](int di) { return fit_shard(p, di, shard[di], delays, P, theta0, o, out); });
 }
 
@@ -438,6 +536,8 @@ int gpcc_ctx_create(int ndev, const int* dev_ids, gpcc_ctx** out) {
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaEventCreate(&s.fit_ev0));
+        CUDA_TRY(cudaEventCreate(&s.fit_ev1));
         CUDA_TRY(cudaEventCreate(&s.origin));
         CUDA_TRY(cudaEventRecord(s.origin, s.stream));
         CUDA_TRY(cudaEventSynchronize(s.origin));
@@ -458,11 +558,16 @@ int gpcc_ctx_destroy(gpcc_ctx* ctx) {
         cudaSetDevice(s.dev);
         for (auto& q : s.slot) {
             s.post_ll.release(); s.post_prior.release(); s.post_out.release();
+            s.gat_send.release(); s.gat_recv.release(); s.gat_post.release();
             q.delays.release(); q.alpha.release(); q.rho.release(); q.ll.release(); q.grad.release(); q.info.release();
             if (q.ev0) cudaEventDestroy(q.ev0);
             if (q.ev1) cudaEventDestroy(q.ev1);
             if (q.done) cudaEventDestroy(q.done);
         }
+        s.fit_delays.release(); s.fit_theta0.release(); s.fit_ll.release(); s.fit_theta.release();
+        s.fit_iters.release(); s.fit_nfev.release(); s.fit_status.release(); s.fit_counters.release(); s.fit_order.release();
+        if (s.fit_ev0) cudaEventDestroy(s.fit_ev0);
+        if (s.fit_ev1) cudaEventDestroy(s.fit_ev1);
         large_workspace_release(s.large);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.stream2) cudaStreamDestroy(s.stream2);
@@ -698,16 +803,53 @@ int gpcc_grid_posterior(gpcc_problem* p, int M, const double* delays, const doub
     if (M < 1 || P < 1) return fail(-2, "need M >= 1 and P >= 1");
     Timer tm;
     reset_stats(p->ctx);
-    std::vector<double> ll_local;
-    double* ll = out_ll;
-    if (!ll) { ll_local.resize(M); ll = ll_local.data(); }
-    FitOutputs out{ll, out_theta, out_alpha, out_rho, nullptr, out_nfev, out_info};
+    const int L = p->L, n = L + 1;
+    // every output is needed internally: with several ranks the all-gather carries the whole record of a candidate
+    std::vector<double> ll_l, th_l, al_l, rh_l;
+    std::vector<int> nf_l, in_l;
+    GatherIO io;
+    io.ll = out_ll ? out_ll : (ll_l.resize(M), ll_l.data());
+    io.theta = out_theta ? out_theta : (th_l.resize((size_t)M * n), th_l.data());
+    io.alpha = out_alpha ? out_alpha : (al_l.resize((size_t)M * L), al_l.data());
+    io.rho = out_rho ? out_rho : (rh_l.resize(M), rh_l.data());
+    io.nfev = out_nfev ? out_nfev : (nf_l.resize(M), nf_l.data());
+    io.info = out_info ? out_info : (in_l.resize(M), in_l.data());
+    FitOutputs out{io.ll, io.theta, io.alpha, io.rho, nullptr, io.nfev, io.info};
     rc = fit_all(p, M, delays, P, theta0, *opt, out);
     if (rc) return rc;
-    // allgather of the per-device slices (NCCL when the context spans several devices) + log-sum-exp on device
-    rc = posterior_on_devices(p->ctx, M, ll, logprior, out_post);
+    // all-gather of the per-device slices (NCCL when the grid spans several devices or ranks) + log-sum-exp on device
+    rc = posterior_on_devices(p->ctx, L, M, io, logprior, out_post);
+    if (rc) return rc;
+    if (p->ctx->world > 1)        // alpha, rho of the other ranks' candidates follow from their gathered theta (unpack, :235)
+        for (int m = 0; m < M; ++m) {
+            if (io.info[m] == LbfgsState::NO_START) {
+                for (int l = 0; l < L; ++l) io.alpha[(size_t)m * L + l] = std::numeric_limits<double>::quiet_NaN();
+                io.rho[m] = std::numeric_limits<double>::quiet_NaN();
+            } else unpack_theta(io.theta + (size_t)m * n, L, *opt, io.alpha + (size_t)m * L, io.rho + m, nullptr);
+        }
     collect_stats(p->ctx, p, tm.ms());
     return rc;
+}
+
+int gpcc_comm_unique_id(char* out_id128) {
+    if (!out_id128) return fail(-1, "NULL argument");
+    std::string err;
+    if (nccl_bridge_unique_id(out_id128, err)) return fail(2000, "NCCL unavailable: " + err);
+    return 0;
+}
+
+int gpcc_ctx_comm_init_rank(gpcc_ctx* ctx, int world, int rank, const char* id128) {
+    if (!ctx || !id128) return fail(-1, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(-2, "need 0 <= rank < world");
+    if (ctx->ds.size() != 1) return fail(-3, "a context that joins a multi-process communicator must own exactly one device");
+    if (ctx->nccl) { nccl_bridge_destroy(ctx->nccl); ctx->nccl = nullptr; }
+    ctx->world = 1; ctx->rank = 0;
+    if (world == 1) return 0;
+    std::string err;
+    ctx->nccl = nccl_bridge_create_rank(ctx->ds[0].dev, world, rank, id128, err);
+    if (!ctx->nccl) return fail(2000, "NCCL unavailable for the multi-process allgather: " + err);
+    ctx->world = world; ctx->rank = rank;
+    return 0;
 }
 
 int gpcc_getprobabilities(gpcc_ctx* ctx, int M, const double* loglik, const double* logprior, double* out_post) {
@@ -738,12 +880,17 @@ int gpcc_getprobabilities(gpcc_ctx* ctx, int M, const double* loglik, const doub
 // ---- posterior over the grid: allgather + log-sum-exp ---------------------------------------------------
 namespace gpcc {
 
-int posterior_on_devices(gpcc_ctx* ctx, int M, const double* ll, const double* logprior, double* out_post) {
+int posterior_on_devices(gpcc_ctx* ctx, int L, int M, const GatherIO& io, const double* logprior, double* out_post) {
     const int nd = (int)ctx->ds.size();
-    if (nd == 1) return gpcc_getprobabilities(ctx, M, ll, logprior, out_post);
-    // Each device owns the strided slice m = di, di+nd, ... ; pad to a common length, allgather over NVLink,
-    // then device 0 normalises (src/getprobabilities.jl:14-16).
-    const int per = (M + nd - 1) / nd;
+    const int G = ctx->world * nd;
+    if (G == 1) return gpcc_getprobabilities(ctx, M, io.ll, logprior, out_post);
+    // Global device g owns the strided slice m = g, g+G, ...  Every device packs its slice into records
+    //   [loglik, joint = loglik + logprior, theta (L+1), nfev, info]
+    // padded to a common length, reduces the joint column to (max, sum exp) on the device, and ONE ncclAllGather over
+    // NVLink distributes records and partials; the combine after it is G elements (src/getprobabilities.jl:14-16).
+    const int n = L + 1, REC = n + 4, JCOL = 1;
+    const int per = (M + G - 1) / G;
+    const size_t blk = (size_t)per * REC + 2;
     if (!ctx->nccl) {
         std::vector<int> devs;
         for (auto& s : ctx->ds) devs.push_back(s.dev);
@@ -751,44 +898,57 @@ int posterior_on_devices(gpcc_ctx* ctx, int M, const double* ll, const double* l
         ctx->nccl = nccl_bridge_create(devs, err);
         if (!ctx->nccl) return fail(2000, "NCCL unavailable for the multi-device allgather: " + err);
     }
-    std::vector<double*> d_send(nd, nullptr), d_recv(nd, nullptr);
+    std::vector<double*> d_send(nd), d_recv(nd);
     std::vector<cudaStream_t> streams(nd);
     const double ninf = -std::numeric_limits<double>::infinity();
     for (int di = 0; di < nd; ++di) {
         DeviceState& s = ctx->ds[di];
         CUDA_TRY(cudaSetDevice(s.dev));
-        CUDA_TRY(cudaMalloc(&d_send[di], per * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&d_recv[di], (size_t)per * nd * sizeof(double)));
-        std::vector<double> slice(per, ninf);
+        CUDA_TRY(s.gat_send.reserve(blk));
+        CUDA_TRY(s.gat_recv.reserve(blk * G));
+        const int g = ctx->rank * nd + di;
+        double* h = s.gat_send.h;
         for (int k = 0; k < per; ++k) {
-            const int m = di + k * nd;
-            if (m < M) slice[k] = ll[m] + (logprior ? logprior[m] : 1.0);      // joint (getprobabilities.jl:3,14)
+            const int m = g + k * G;
+            double* r = h + (size_t)k * REC;
+            if (m < M) {
+                r[0] = io.ll[m];
+                r[1] = io.ll[m] + (logprior ? logprior[m] : 1.0);            // joint (getprobabilities.jl:3,14)
+                std::memcpy(r + 2, io.theta + (size_t)m * n, n * sizeof(double));
+                r[2 + n] = (double)io.nfev[m];
+                r[3 + n] = (double)io.info[m];
+            } else {
+                r[0] = ninf; r[1] = ninf;
+                for (int q = 2; q < REC; ++q) r[q] = 0.0;
+            }
         }
-        CUDA_TRY(cudaMemcpyAsync(d_send[di], slice.data(), per * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaStreamSynchronize(s.stream));
-        streams[di] = s.stream;
+        CUDA_TRY(cudaMemcpyAsync(s.gat_send.d, h, (size_t)per * REC * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(posterior_partial_launch(per, REC, JCOL, s.gat_send.d, s.stream));
+        d_send[di] = s.gat_send.d; d_recv[di] = s.gat_recv.d; streams[di] = s.stream;
     }
     std::string err;
-    if (nccl_bridge_allgather(ctx->nccl, d_send, d_recv, per, streams, err)) return fail(2001, "ncclAllGather: " + err);
-    // gathered layout: [rank][k] -> candidate m = rank + k*nd
+    if (nccl_bridge_allgather(ctx->nccl, d_send, d_recv, (int)blk, streams, err)) return fail(2001, "ncclAllGather: " + err);
     DeviceState& s0 = ctx->ds[0];
     CUDA_TRY(cudaSetDevice(s0.dev));
-    double* d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_out, (size_t)per * nd * sizeof(double)));
-    CUDA_TRY(posterior_launch(per * nd, d_recv[0], nullptr, d_out, s0.stream, /*joint_already=*/true));
-    std::vector<double> tmp((size_t)per * nd);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+    CUDA_TRY(s0.gat_post.reserve((size_t)per * G));
+    CUDA_TRY(posterior_combine_launch(G, per, REC, JCOL, s0.gat_recv.d, s0.gat_post.d, s0.stream));
+    CUDA_TRY(cudaMemcpyAsync(s0.gat_post.h, s0.gat_post.d, (size_t)per * G * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+    CUDA_TRY(cudaMemcpyAsync(s0.gat_recv.h, s0.gat_recv.d, blk * G * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
     CUDA_TRY(cudaStreamSynchronize(s0.stream));
-    for (int di = 0; di < nd; ++di)
+    for (int g = 0; g < G; ++g)
         for (int k = 0; k < per; ++k) {
-            const int m = di + k * nd;
-            if (m < M) out_post[m] = tmp[(size_t)di * per + k];
+            const int m = g + k * G;
+            if (m >= M) continue;
+            out_post[m] = s0.gat_post.h[(size_t)g * per + k];
+            if (ctx->world > 1) {      // the other ranks' candidates arrive through the gather
+                const double* r = s0.gat_recv.h + g * blk + (size_t)k * REC;
+                io.ll[m] = r[0];
+                std::memcpy(io.theta + (size_t)m * n, r + 2, n * sizeof(double));
+                io.nfev[m] = (int)r[2 + n];
+                io.info[m] = (int)r[3 + n];
+            }
         }
-    cudaFree(d_out);
-    for (int di = 0; di < nd; ++di) {
-        cudaSetDevice(ctx->ds[di].dev);
-        cudaFree(d_send[di]); cudaFree(d_recv[di]);
-    }
+    for (auto& s : ctx->ds) s.launches += 2;
     return 0;
 }
 

@@ -32,9 +32,7 @@ struct EvalBatch {
     double* ll = nullptr;            // [M]
     double* grad = nullptr;          // [M][L+1]
     int* info = nullptr;             // [M]
-    double* dump_kinv = nullptr;     // optional [M][N*N] dense column-major K~^-1 (both triangles)
-    double* dump_a = nullptr;        // optional [M][N]   a = K~^-1 (Y - bbar)
-    int mode_postb = 0;              // 1: factor Sobs + K WITHOUT B and solve against Y (postb, :248-250)
+    int mode_postb = 0;              // 1 (tiled path only): factor Sobs + K WITHOUT B (the fitted state of postb / pred, :241-250)
     double* dump_chol = nullptr;     // optional [M][N*N] dense column-major Cholesky factor (lower, upper part zero); tiled path,
                                      // forward mode only (the fitted state behind postb / pred, fitstate.cu)
 };
@@ -45,17 +43,30 @@ constexpr int SMALL_TILE = 8;
 constexpr int SMALL_MAX_T = 25;
 inline bool small_path_supports(int N) { return (N + 1 + SMALL_TILE - 1) / SMALL_TILE <= SMALL_MAX_T; }
 cudaError_t small_sweep_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
-cudaError_t small_sweep_init();   // sets max dynamic shared memory attributes once per device
-// blocked (eight pivots per step) form of the fused evaluator (small_block.cu)
-bool small_block_supports(int N);
-cudaError_t small_block_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
-// fragment-layout form: tiles spread over warps, DMMA for panel and update, several matrices per CTA (small_frag.cu)
-bool small_frag_supports(int N);
-cudaError_t small_frag_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
-// tensor-pipe variant of the fused evaluator (small_dmma.cu)
-bool small_dmma_supports(int N);
-cudaError_t small_dmma_launch(const DevProblem& p, const EvalBatch& b, cudaStream_t stream);
 
+// ---- device-resident fit of the fused small-N path (small_fit.cu): screening + L-BFGS without leaving the kernel ----
+struct FitParams {            // keyword arguments / constants of gpcc (gpccfixdelay_marginaliseb.jl:46, :112, :205)
+    int M = 0;                // candidates of this launch
+    int P = 0;                // start points per candidate (`initialrandom`)
+    int theta0_per_candidate = 0;
+    int max_iter = 1000;
+    double rhomin = 0.1, rhomax = 20.0, alpha_floor = 1e-8, gtol = 1e-7, ftol = 1e-13;
+    int history = 8;
+    int screen_forward = 1;   // 1: screen with forward-only evaluations (N^3/3) and evaluate the gradient at the winner only
+};
+struct FitBuffers {           // all on the device
+    const double* delays = nullptr;   // [M][L]
+    const double* theta0 = nullptr;   // [P][L+1] or [M][P][L+1]
+    const int* order = nullptr;       // [M] work-queue order: position q of the queue is candidate order[q]
+    double* ll = nullptr;             // [M]  -result.minimum (:351)
+    double* theta = nullptr;          // [M][L+1]
+    int* iters = nullptr;             // [M]
+    int* nfev = nullptr;              // [M]  objective evaluations as the optimiser counts them
+    int* status = nullptr;            // [M]  LbfgsState::Status
+    unsigned long long* counters = nullptr;   // [8]: [0] work queue head, [1] evaluations with gradient, [2] forward-only evaluations,
+                                              // [3] sum over CTAs of (exit - first start) ns, [4] last exit, [5] first start, [6] CTAs
+};
+cudaError_t small_fit_launch(const DevProblem& p, const FitParams& fp, const FitBuffers& fb, cudaStream_t stream);
 
 // ---- large-N path: tiled matrix in HBM, blocked sweep with DMMA trailing updates (large_path.cu) --
 struct LargeWorkspace {
@@ -72,10 +83,17 @@ void large_workspace_release(LargeWorkspace& ws);
 // ---- posterior over candidates (posterior.cu): src/getprobabilities.jl:10-20 --------------------
 cudaError_t posterior_launch(int M, const double* d_ll, const double* d_logprior, double* d_out, cudaStream_t stream,
                              bool joint_already = false);
+// sharded form: every device reduces its own slice to (max, sum exp) before the all-gather, the combine after it is G elements
+//   send  [per][rec] records with the joint log-density in column `jcol`, followed by 2 doubles for the partials
+cudaError_t posterior_partial_launch(int per, int rec, int jcol, double* d_send, cudaStream_t stream);
+//   recv  G blocks of (per*rec + 2) doubles as gathered; out[g*per + k] = exp(joint - logsumexp)
+cudaError_t posterior_combine_launch(int G, int per, int rec, int jcol, const double* d_recv, double* d_out, cudaStream_t stream);
 
 // ---- NCCL, loaded at run time so that single-GPU use needs no NCCL at all (nccl_bridge.cpp) -------
 struct NcclBridge;
 NcclBridge* nccl_bridge_create(const std::vector<int>& devs, std::string& err);
+int nccl_bridge_unique_id(char* out128, std::string& err);
+NcclBridge* nccl_bridge_create_rank(int dev, int world, int rank, const char* id128, std::string& err);
 void nccl_bridge_destroy(NcclBridge* b);
 int nccl_bridge_allgather(NcclBridge* b, const std::vector<double*>& send, const std::vector<double*>& recv, int count,
                           const std::vector<cudaStream_t>& streams, std::string& err);
@@ -84,5 +102,9 @@ int nccl_bridge_allgather(NcclBridge* b, const std::vector<double*>& send, const
 
 struct gpcc_ctx;
 namespace gpcc {
-int posterior_on_devices(gpcc_ctx* ctx, int M, const double* ll, const double* logprior, double* out_post);
+struct GatherIO {      // per-candidate outputs of a grid fit, host arrays of the caller (any may be NULL except ll)
+    double *ll, *theta, *alpha, *rho;
+    int *nfev, *info;
+};
+int posterior_on_devices(gpcc_ctx* ctx, int L, int M, const GatherIO& io, const double* logprior, double* out_post);
 }

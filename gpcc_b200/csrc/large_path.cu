@@ -650,21 +650,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(DevProblem p, EvalBatch b
     }
 }
 
-// dense column-major K^-1 (both triangles) and a, for postb / pred
-__global__ void dump_kernel(EvalBatch b, int e0, LargeArgs a) {
-    const int m = blockIdx.y, e = e0 + m;
-    const double* mat = a.mats + (size_t)m * a.mat_stride;
-    double* out = b.dump_kinv + (size_t)e * a.N * a.N;
-    const size_t total = (size_t)a.N * a.N;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(q % a.N), j = (int)(q / a.N);
-        const int r = i >= j ? i : j, c = i >= j ? j : i;
-        out[q] = -mat[tile_index(r >> 7, c >> 7) * TILE_ELEMS + tl_off(r & 127, c & 127)];
-    }
-    if (b.dump_a && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < a.N; i += blockDim.x) b.dump_a[(size_t)e * a.N + i] = a.rvec[(size_t)m * a.Np + i];
-}
-
 // dense column-major Cholesky factor (lower triangle, zeros above) out of the tile layout: forward mode only
 __global__ void dump_chol_kernel(EvalBatch b, int e0, LargeArgs a) {
     const int m = blockIdx.y, e = e0 + m;
@@ -746,7 +731,7 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, La
                      LargeTimings* tm) {
     LargeArgs a;
     a.N = p.N; a.L = p.L; a.T = w.T; a.Np = w.Np; a.kid = KID;
-    a.sweep = (b.want_grad || b.dump_kinv) ? 1 : 0;
+    a.sweep = b.want_grad ? 1 : 0;
     a.mode_postb = b.mode_postb;
     a.mats = w.mats; a.Pws = w.Pws; a.Xws = w.Xws; a.Linv = w.Linv; a.Dinv = w.Dinv; a.rvec = w.rvec; a.zk = w.zk;
     a.scal = w.scal; a.info = w.info; a.tsh = w.tsh; a.av = w.av; a.part = w.part; a.epart = w.epart; a.mat_stride = w.mat_stride;
@@ -813,10 +798,6 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, La
     }
     finalize_kernel<<<nb, 256, 0, st>>>(p, b, e0, a);
     ++launches;
-    if (b.dump_kinv) {
-        dump_kernel<<<dim3(592, nb), 256, 0, st>>>(b, e0, a);
-        ++launches;
-    }
     if (b.dump_chol && !a.sweep) {
         dump_chol_kernel<<<dim3(592, nb), 256, 0, st>>>(b, e0, a);
         ++launches;

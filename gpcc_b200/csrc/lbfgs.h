@@ -1,14 +1,25 @@
-// Host-driven batched L-BFGS: one small state machine per delay candidate; every round the driver
-// gathers the trial points of all active candidates into ONE batched device evaluation
-// (likelihood + analytic gradient) and feeds the results back.  Replaces the per-candidate
+// Batched L-BFGS: one small state machine per delay candidate.  Replaces the per-candidate
 // optimize(..., NelderMead(), ...) of /root/reference/src/gpccfixdelay_marginaliseb.jl:205-211
 // as north_star specifies.  Minimises f = -logL over the unconstrained theta in R^(L+1).
+// The same code runs in two drivers:
+//   * on the DEVICE (small_fit.cu): one persistent CTA per candidate keeps this state in shared memory and alternates
+//     evaluation and update without leaving the kernel (fused small-N path, the default);
+//   * on the host (api.cu, fit_shard): every round gathers the trial points of all active candidates into ONE batched
+//     device evaluation and feeds the results back (tiled large-N path, where one evaluation is many kernels).
 #pragma once
 #include <cmath>
-#include <cstring>
-#include <limits>
+
+#if defined(__CUDACC__)
+#define GPCC_HD __host__ __device__
+#else
+#define GPCC_HD
+#endif
 
 namespace gpcc {
+
+GPCC_HD inline bool lb_finite(double x) { return x - x == 0.0; }          // false for +-Inf and NaN
+GPCC_HD inline double lb_inf() { return __builtin_huge_val(); }
+GPCC_HD inline void lb_copy(double* dst, const double* src, int n) { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
 
 constexpr int LBFGS_MAXN = 9;    // L+1 <= GPCC_MAX_BANDS+1
 constexpr int LBFGS_MAXM = 16;
@@ -38,29 +49,29 @@ struct LbfgsState {
     int hcount = 0, hhead = 0;         // ring buffer
     int small_df = 0;
 
-    static double dot(const double* a, const double* b, int n) {
+    GPCC_HD static double dot(const double* a, const double* b, int n) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) s += a[i] * b[i];
         return s;
     }
 
-    void start(int n_, const double* x0, double f0, const double* g0, const LbfgsOptions& o) {
+    GPCC_HD void start(int n_, const double* x0, double f0, const double* g0, const LbfgsOptions& o) {
         n = n_;
-        std::memcpy(x, x0, n * sizeof(double));
-        std::memcpy(g, g0, n * sizeof(double));
+        lb_copy(x, x0, n);
+        lb_copy(g, g0, n);
         f = f0;
         status = RUNNING;
         iters = 0;
         hcount = hhead = 0;
         small_df = 0;
         double gmax = 0.0;
-        for (int i = 0; i < n; ++i) gmax = std::fmax(gmax, std::fabs(g[i]));
+        for (int i = 0; i < n; ++i) gmax = fmax(gmax, fabs(g[i]));
         if (!(gmax > o.gtol)) { status = CONVERGED; return; }
         if (o.max_iter <= 0) { status = ITER_CAP; return; }
         new_direction(true);
     }
 
-    void new_direction(bool first) {
+    GPCC_HD void new_direction(bool first) {
         // two-loop recursion
         double qv[LBFGS_MAXN], a[LBFGS_MAXM];
         for (int i = 0; i < n; ++i) qv[i] = g[i];
@@ -81,7 +92,7 @@ struct LbfgsState {
         }
         for (int i = 0; i < n; ++i) d[i] = -qv[i];
         gd0 = dot(g, d, n);
-        if (!(gd0 < 0.0) || !std::isfinite(gd0)) {     // not a descent direction: restart from steepest descent
+        if (!(gd0 < 0.0) || !lb_finite(gd0)) {     // not a descent direction: restart from steepest descent
             hcount = 0;
             for (int i = 0; i < n; ++i) d[i] = -g[i];
             gd0 = dot(g, d, n);
@@ -89,43 +100,43 @@ struct LbfgsState {
         }
         t = 1.0;
         if (first || hcount == 0) {
-            const double gn = std::sqrt(dot(g, g, n));
-            t = std::fmin(1.0, 1.0 / gn);
+            const double gn = sqrt(dot(g, g, n));
+            t = fmin(1.0, 1.0 / gn);
         }
         // Cap the step at STEP_CAP units of the unconstrained parameters per iteration.  theta lives on the softplus /
         // logistic scale: a jump of many units lands where the transforms saturate (alpha -> floor, rho -> rhomin), their
         // Jacobians vanish and a gradient method crawls for hundreds of iterations in a degenerate basin.
         double dmax = 0.0;
-        for (int i = 0; i < n; ++i) dmax = std::fmax(dmax, std::fabs(d[i]));
-        tcap = dmax > 0.0 ? STEP_CAP / dmax : std::numeric_limits<double>::infinity();
-        t = std::fmin(t, tcap);
+        for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(d[i]));
+        tcap = dmax > 0.0 ? STEP_CAP / dmax : lb_inf();
+        t = fmin(t, tcap);
         tlo = 0.0;
-        thi = std::numeric_limits<double>::infinity();
+        thi = lb_inf();
         ls_trials = 0;
         have_fb = false;
         for (int i = 0; i < n; ++i) xt[i] = x[i] + t * d[i];
     }
 
-    void accept(const double* xn, double fn, const double* gn, const LbfgsOptions& o, int hist) {
+    GPCC_HD void accept(const double* xn, double fn, const double* gn, const LbfgsOptions& o, int hist) {
         double s[LBFGS_MAXN], y[LBFGS_MAXN];
         for (int i = 0; i < n; ++i) { s[i] = xn[i] - x[i]; y[i] = gn[i] - g[i]; }
         const double sy = dot(s, y, n);
-        if (sy > 1e-10 * std::sqrt(dot(s, s, n) * dot(y, y, n)) && sy > 0.0) {
-            std::memcpy(S[hhead], s, n * sizeof(double));
-            std::memcpy(Y[hhead], y, n * sizeof(double));
+        if (sy > 1e-10 * sqrt(dot(s, s, n) * dot(y, y, n)) && sy > 0.0) {
+            lb_copy(S[hhead], s, n);
+            lb_copy(Y[hhead], y, n);
             R[hhead] = 1.0 / sy;
             hhead = (hhead + 1) % LBFGS_MAXM;
             if (hcount < hist) ++hcount;
         }
         const double df = f - fn;
-        std::memcpy(x, xn, n * sizeof(double));
-        std::memcpy(g, gn, n * sizeof(double));
+        lb_copy(x, xn, n);
+        lb_copy(g, gn, n);
         f = fn;
         ++iters;
         double gmax = 0.0;
-        for (int i = 0; i < n; ++i) gmax = std::fmax(gmax, std::fabs(g[i]));
+        for (int i = 0; i < n; ++i) gmax = fmax(gmax, fabs(g[i]));
         if (gmax <= o.gtol) { status = CONVERGED; return; }
-        if (df <= o.ftol * std::fmax(1.0, std::fabs(f))) { if (++small_df >= 2) { status = CONVERGED; return; } }
+        if (df <= o.ftol * fmax(1.0, fabs(f))) { if (++small_df >= 2) { status = CONVERGED; return; } }
         else small_df = 0;
         if (iters >= o.max_iter) { status = ITER_CAP; return; }
         new_direction(false);
@@ -137,45 +148,45 @@ struct LbfgsState {
 
     // Feed the evaluation at xt (ok=false: matrix not PD / non-finite).  Afterwards either status != RUNNING
     // or xt holds the next trial point.
-    void feed(bool ok, double ft, const double* gt, const LbfgsOptions& o) {
+    GPCC_HD void feed(bool ok, double ft, const double* gt, const LbfgsOptions& o) {
         ++nfev;
         ++ls_trials;
         const int hist = o.history < 1 ? 1 : (o.history > LBFGS_MAXM ? LBFGS_MAXM : o.history);
         const double c1 = 1e-4, c2 = 0.9;
-        bool armijo = ok && std::isfinite(ft) && ft <= f + c1 * t * gd0;
+        bool armijo = ok && lb_finite(ft) && ft <= f + c1 * t * gd0;
         if (armijo) {
             const double gtd = dot(gt, d, n);
             if (gtd >= c2 * gd0) { accept(xt, ft, gt, o, hist); return; }   // weak Wolfe holds
-            if (std::isinf(thi) && t >= tcap) { accept(xt, ft, gt, o, hist); return; }   // sufficient decrease at the step cap
+            if ((thi == lb_inf()) && t >= tcap) { accept(xt, ft, gt, o, hist); return; }   // sufficient decrease at the step cap
             if (!have_fb || ft < fb_f) {
                 have_fb = true; fb_f = ft;
-                std::memcpy(fb_x, xt, n * sizeof(double));
-                std::memcpy(fb_g, gt, n * sizeof(double));
+                lb_copy(fb_x, xt, n);
+                lb_copy(fb_g, gt, n);
             }
             tlo = t;
-            t = std::isinf(thi) ? std::fmin(2.0 * t, tcap) : 0.5 * (tlo + thi);
+            t = (thi == lb_inf()) ? fmin(2.0 * t, tcap) : 0.5 * (tlo + thi);
         } else {
             // The objective carries ~1e-13 relative rounding noise.  Once the decrease the model predicts for this step is
             // below that noise, Armijo can no longer be verified and further backtracking only burns evaluations: the
             // point is converged to within the noise (remaining improvement <= |t g'd|, far below the 1e-6 target).
-            const double noise = 4e-13 * std::fmax(1.0, std::fabs(f));
-            if (ok && std::isfinite(ft) && std::fabs(ft - f) <= noise && -t * gd0 <= noise) {
+            const double noise = 4e-13 * fmax(1.0, fabs(f));
+            if (ok && lb_finite(ft) && fabs(ft - f) <= noise && -t * gd0 <= noise) {
                 if (have_fb && fb_f < f) { accept(fb_x, fb_f, fb_g, o, hist); if (status == RUNNING) status = CONVERGED; return; }
                 status = CONVERGED;
                 return;
             }
             thi = t;
             double tn = 0.5 * (tlo + thi);
-            if (tlo == 0.0 && ok && std::isfinite(ft)) {     // quadratic interpolation through f(0), f'(0), f(t)
+            if (tlo == 0.0 && ok && lb_finite(ft)) {     // quadratic interpolation through f(0), f'(0), f(t)
                 const double den = 2.0 * (ft - f - gd0 * t);
                 if (den > 0.0) {
                     const double tq = -gd0 * t * t / den;
-                    tn = std::fmin(std::fmax(tq, 0.1 * t), 0.5 * t);
+                    tn = fmin(fmax(tq, 0.1 * t), 0.5 * t);
                 }
             }
             t = tn;
         }
-        if (ls_trials >= o.max_ls || !(thi - tlo > 1e-16 * std::fmax(1.0, thi))) {
+        if (ls_trials >= o.max_ls || !(thi - tlo > 1e-16 * fmax(1.0, thi))) {
             if (have_fb && fb_f < f) { accept(fb_x, fb_f, fb_g, o, hist); return; }
             status = LS_STALL;
             return;

@@ -66,6 +66,12 @@ struct DeviceState {
     double busy_end_ms = 0;           // end of the last kernel interval counted so far, relative to `origin`
     EvalSlot slot[2];
     DevBuf<double> post_ll, post_prior, post_out;   // persistent staging of the posterior kernel (no cudaMalloc/cudaFree per call)
+    // staging of the device-resident fit (small_fit.cu)
+    DevBuf<double> fit_delays, fit_theta0, fit_ll, fit_theta;
+    DevBuf<int> fit_iters, fit_nfev, fit_status, fit_order;
+    DevBuf<unsigned long long> fit_counters;
+    DevBuf<double> gat_send, gat_recv, gat_post;     // all-gather of the grid results (persistent: no cudaMalloc per call)
+    cudaEvent_t fit_ev0 = nullptr, fit_ev1 = nullptr;
     LargeWorkspace large;     // tiled large-N path (large_path.cu)
     // per-call statistics (profiling)
     double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
@@ -79,6 +85,7 @@ struct gpcc_ctx {
     bool profiling = false;
     gpcc_stats stats{};
     gpcc::NcclBridge* nccl = nullptr;
+    int world = 1, rank = 0;      // > 1 ranks: one process per device, joined by gpcc_ctx_comm_init_rank
 };
 
 struct gpcc_fit_state;
@@ -101,12 +108,10 @@ struct gpcc_problem {
 
 namespace gpcc {
 // Evaluate M (delay, alpha, rho) triples already staged in the pinned mirrors of device `di`;
-// results land in ds[di].ll.h / grad.h / info.h.  Optionally dumps K~^-1 (dense) and a = K~^-1 r.
-int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad, double* dump_kinv = nullptr,
-                       double* dump_a = nullptr, int mode_postb = 0);
+// results land in ds[di].ll.h / grad.h / info.h.
+int evaluate_on_device(gpcc_problem* p, int di, int M, int want_grad);
 int reserve_eval(gpcc_problem* p, int di, size_t M, int slot = 0);
 // asynchronous pair: launch_eval enqueues H2D + kernel + D2H of slot `slot`; finish_eval waits for it.
-int launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad, double* dump_kinv = nullptr, double* dump_a = nullptr,
-                int mode_postb = 0);
+int launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad);
 int finish_eval(gpcc_problem* p, int di, int slot);
 }  // namespace gpcc

@@ -76,6 +76,12 @@ const char* gpcc_last_error(void);
  * log-likelihoods are combined with one NCCL allgather.                                             */
 int gpcc_ctx_create(int ndev, const int* dev_ids, gpcc_ctx** out);
 int gpcc_ctx_destroy(gpcc_ctx* ctx);
+/* One process per GPU (torchrun; one Julia `Distributed` worker per device, README.md:185-189): rank 0 draws an id,
+ * the host program hands its 128 bytes to every rank, and each rank attaches its ONE-device context.  From then on
+ * gpcc_fit_batch fits only the candidates m with m mod world == rank, and gpcc_grid_posterior (called by EVERY rank with
+ * the same arguments) all-gathers the per-candidate records over NCCL and returns the full outputs on every rank.   */
+int gpcc_comm_unique_id(char* out_id128);
+int gpcc_ctx_comm_init_rank(gpcc_ctx* ctx, int world, int rank, const char* id128);
 int gpcc_ctx_set_profiling(gpcc_ctx* ctx, int enabled);
 int gpcc_ctx_get_stats(const gpcc_ctx* ctx, gpcc_stats* out);
 int gpcc_ctx_device_count(const gpcc_ctx* ctx);
