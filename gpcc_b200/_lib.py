@@ -20,7 +20,8 @@ EXPORTS = [
 class FitOptions(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("rhomin", C.c_double), ("rhomax", C.c_double),
                 ("alpha_floor", C.c_double), ("gtol", C.c_double), ("ftol", C.c_double),
-                ("history", C.c_int), ("transform_id", C.c_int), ("theta0_per_candidate", C.c_int)]
+                ("history", C.c_int), ("transform_id", C.c_int), ("theta0_per_candidate", C.c_int),
+                ("optimizer", C.c_int), ("nm_gtol", C.c_double)]
 
 
 class Stats(C.Structure):

@@ -149,7 +149,10 @@ def default_context():
     return _default_ctx
 
 
-def _options(iterations, rhomin, rhomax, per_candidate=False, gtol=None, ftol=None, history=None):
+_OPTIMIZERS = {"lbfgs": 0, "neldermead": 1}
+
+
+def _options(iterations, rhomin, rhomax, per_candidate=False, gtol=None, ftol=None, history=None, optimizer="lbfgs"):
     o = FitOptions()
     check(_lib.load().gpcc_fit_options_default(C.byref(o)))
     o.max_iter, o.rhomin, o.rhomax = int(iterations), float(rhomin), float(rhomax)
@@ -160,6 +163,9 @@ def _options(iterations, rhomin, rhomax, per_candidate=False, gtol=None, ftol=No
         o.ftol = ftol
     if history is not None:
         o.history = history
+    if optimizer not in _OPTIMIZERS:
+        raise GpccError("optimizer must be 'lbfgs' (default) or 'neldermead' (the reference's, on the device)")
+    o.optimizer = _OPTIMIZERS[optimizer]
     return o
 
 
@@ -225,13 +231,13 @@ class Problem:
         return (ll, grad, info) if want_grad else (ll, info)
 
     # ---- fit (:203-226) ------------------------------------------------------------------------------
-    def fit_batch(self, delays, theta0, *, iterations, rhomin, rhomax, gtol=None, ftol=None, history=None):
+    def fit_batch(self, delays, theta0, *, iterations, rhomin, rhomax, gtol=None, ftol=None, history=None, optimizer="lbfgs"):
         delays = _f64(delays, (-1, self.L))
         M = delays.shape[0]
         theta0 = _f64(theta0)
         per_cand = theta0.ndim == 3
         P = theta0.shape[-2]
-        o = _options(iterations, rhomin, rhomax, per_cand, gtol, ftol, history)
+        o = _options(iterations, rhomin, rhomax, per_cand, gtol, ftol, history, optimizer)
         res = dict(loglikel=np.empty(M), theta=np.empty((M, self.L + 1)), alpha=np.empty((M, self.L)), rho=np.empty(M),
                    iters=np.empty(M, dtype=np.int32), nfev=np.empty(M, dtype=np.int32), info=np.empty(M, dtype=np.int32))
         check(_lib.load().gpcc_fit_batch(self._h, M, _d(delays), P, _d(theta0), C.byref(o), _d(res["loglikel"]),
@@ -239,13 +245,13 @@ class Problem:
                                          _i(res["nfev"]), _i(res["info"])))
         return res
 
-    def grid_posterior(self, delays, theta0, *, iterations, rhomin, rhomax, logprior=None, gtol=None, ftol=None):
+    def grid_posterior(self, delays, theta0, *, iterations, rhomin, rhomax, logprior=None, gtol=None, ftol=None, optimizer="lbfgs"):
         delays = _f64(delays, (-1, self.L))
         M = delays.shape[0]
         theta0 = _f64(theta0)
         per_cand = theta0.ndim == 3
         P = theta0.shape[-2]
-        o = _options(iterations, rhomin, rhomax, per_cand, gtol, ftol)
+        o = _options(iterations, rhomin, rhomax, per_cand, gtol, ftol, None, optimizer)
         lp = None if logprior is None else _f64(logprior).reshape(M)
         res = dict(loglikel=np.empty(M), posterior=np.empty(M), theta=np.empty((M, self.L + 1)),
                    alpha=np.empty((M, self.L)), rho=np.empty(M), nfev=np.empty(M, dtype=np.int32),
@@ -396,7 +402,7 @@ def _informuser(out, seed, iterations, numberofrestarts, initialrandom, rhomin, 
 
 
 def gpcc(tarray, yarray, stdarray, *, kernel, delays, iterations, seed=1, numberofrestarts=1, initialrandom=5,
-         rhomin=0.1, rhomax, theta0=None, ctx=None, verbose=True, problem=None):
+         rhomin=0.1, rhomax, theta0=None, ctx=None, verbose=True, problem=None, optimizer="lbfgs"):
     """Drop-in for `gpcc` (gpccfixdelay_marginaliseb.jl:46-53): returns (loglikel, pred, (alpha, postb, rho))."""
     p = problem or Problem(tarray, yarray, stdarray, kernel, ctx)
     delays = _f64(delays)
@@ -414,7 +420,7 @@ def gpcc(tarray, yarray, stdarray, *, kernel, delays, iterations, seed=1, number
         theta0 = theta0[None]
     # restarts (:222-226): every restart is one more "candidate" with the same delays and its own start set
     R = theta0.shape[0]
-    res = p.fit_batch(np.tile(delays, (R, 1)), theta0, iterations=iterations, rhomin=rhomin, rhomax=rhomax)
+    res = p.fit_batch(np.tile(delays, (R, 1)), theta0, iterations=iterations, rhomin=rhomin, rhomax=rhomax, optimizer=optimizer)
     best = int(np.argmax(res["loglikel"]))
     loglikel, alpha, rho = float(res["loglikel"][best]), res["alpha"][best].copy(), float(res["rho"][best])
     if verbose:

@@ -48,6 +48,7 @@ int check_options(const gpcc_fit_options* o) {
     if (o->transform_id != GPCC_TRANSFORM_SOFTPLUS_LOGISTIC) return fail(-2, "unknown transform_id");
     if (!(o->rhomin > 0) || !(o->rhomax > o->rhomin)) return fail(-3, "need 0 < rhomin < rhomax");
     if (!(o->alpha_floor >= 0)) return fail(-4, "alpha_floor must be >= 0");
+    if (o->optimizer != GPCC_OPT_LBFGS && o->optimizer != GPCC_OPT_NELDERMEAD) return fail(-5, "unknown optimizer");
     return 0;
 }
 
@@ -244,6 +245,7 @@ int fit_shard_device(gpcc_problem* p, int di, const std::vector<int>& idx, const
     fp.M = m; fp.P = P; fp.theta0_per_candidate = o.theta0_per_candidate; fp.max_iter = o.max_iter;
     fp.rhomin = o.rhomin; fp.rhomax = o.rhomax; fp.alpha_floor = o.alpha_floor; fp.gtol = o.gtol; fp.ftol = o.ftol;
     fp.history = o.history;
+    fp.optimizer = o.optimizer; fp.nm_gtol = o.nm_gtol;
     static const bool screen_full = getenv("GPCC_SCREEN_FULL") != nullptr;     // experiment switch: screen with gradient evaluations
     fp.screen_forward = screen_full ? 0 : 1;
     FitBuffers fb;
@@ -289,7 +291,9 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
     const int m = (int)idx.size();
     if (m == 0) return 0;
     static const bool host_loop = getenv("GPCC_FIT_HOST") != nullptr;          // A/B switch: host-driven batched L-BFGS on the small path
-    if (p->small_path && !host_loop) return fit_shard_device(p, di, idx, delays, P, theta0, o, out);
+    if (p->small_path && (!host_loop || o.optimizer == GPCC_OPT_NELDERMEAD)) return fit_shard_device(p, di, idx, delays, P, theta0, o, out);
+    if (o.optimizer == GPCC_OPT_NELDERMEAD)
+        return fail(-7, "the Nelder-Mead option runs on the fused small-N path only (N <= 199); use the default L-BFGS");
     DeviceState& s = p->ctx->ds[di];
     EvalSlot& q0 = s.slot[0];
     LbfgsOptions lo;
@@ -505,6 +509,8 @@ int gpcc_fit_options_default(gpcc_fit_options* o) {
     o->history = 8;
     o->transform_id = GPCC_TRANSFORM_SOFTPLUS_LOGISTIC;
     o->theta0_per_candidate = 0;
+    o->optimizer = GPCC_OPT_LBFGS;
+    o->nm_gtol = 1e-6;
     return 0;
 }
 

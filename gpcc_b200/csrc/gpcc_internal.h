@@ -52,6 +52,8 @@ struct FitParams {            // keyword arguments / constants of gpcc (gpccfixd
     int max_iter = 1000;
     double rhomin = 0.1, rhomax = 20.0, alpha_floor = 1e-8, gtol = 1e-7, ftol = 1e-13;
     int history = 8;
+    int optimizer = 0;        // 0: L-BFGS on the analytic gradient; 1: Nelder-Mead (nm.h), forward-only evaluations
+    double nm_gtol = 1e-6;    // Optim.Options(g_tol = 1e-6) (:205)
     int screen_forward = 1;   // 1: screen with forward-only evaluations (N^3/3) and evaluate the gradient at the winner only
 };
 struct FitBuffers {           // all on the device

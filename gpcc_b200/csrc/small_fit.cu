@@ -14,6 +14,7 @@
 // one box.  Results do not depend on the schedule: candidates never interact.
 #include "small_eval.cuh"
 #include "lbfgs.h"
+#include "nm.h"
 #include <cstdlib>
 
 namespace gpcc {
@@ -23,6 +24,7 @@ using namespace small;
 
 struct FitCtl {                 // per-CTA control block in shared memory
     LbfgsState S;
+    NmState NM;                 // optimizer = 1 only
     double delays[MAX_BANDS];
     double alpha[MAX_BANDS];    // constrained parameters of the evaluation in flight
     double rho;
@@ -36,7 +38,7 @@ struct FitCtl {                 // per-CTA control block in shared memory
     int cand, phase, j, best, want_grad, fwd;
     unsigned n_grad, n_fwd;
 };
-enum { PH_SCREEN = 0, PH_START = 1, PH_LBFGS = 2, PH_DONE = 3 };
+enum { PH_SCREEN = 0, PH_START = 1, PH_LBFGS = 2, PH_DONE = 3, PH_NM = 4 };
 
 __device__ __forceinline__ double softplus(double x) { return x > 0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
 __device__ __forceinline__ double logistic(double x) { return 0.5 * (1.0 + tanh(0.5 * x)); }
@@ -84,13 +86,28 @@ __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers&
             c.S.f = c.bestf; c.S.status = LbfgsState::ITER_CAP; c.phase = PH_DONE;
             return;
         }
-        if (fp.screen_forward) {                          // gradient at the winner only
+        if (fp.optimizer == 1) {                          // the reference's Nelder-Mead (:205-211): forward-only evaluations
+            c.NM.start(n, c.theta_best, c.bestf, fp.max_iter, fp.nm_gtol);
+            c.phase = PH_NM;
+            if (c.NM.phase != NmState::DONE) {
+                unpack_to_ctl(c, c.NM.xt, L, fp);
+                c.want_grad = 0; c.fwd = 1; ++c.n_fwd;
+                return;
+            }
+        } else if (fp.screen_forward) {                   // gradient at the winner only
             unpack_to_ctl(c, c.theta_best, L, fp);
             c.want_grad = 1; c.fwd = 0; ++c.n_grad;
             c.phase = PH_START;
             return;
         }
-        c.S.start(n, c.theta_best, c.bestf, c.grad_best, lo);
+        if (fp.optimizer != 1) c.S.start(n, c.theta_best, c.bestf, c.grad_best, lo);
+    } else if (c.phase == PH_NM) {                        // result at NM.xt
+        c.NM.feed(c.res_info == 0 && lb_finite(c.res_ll), -c.res_ll, fp.max_iter, fp.nm_gtol);
+        if (c.NM.phase != NmState::DONE) {
+            unpack_to_ctl(c, c.NM.xt, L, fp);
+            c.want_grad = 0; c.fwd = 1; ++c.n_fwd;
+            return;
+        }
     } else if (c.phase == PH_START) {
         double g[LBFGS_MAXN];
         for (int k = 0; k < n; ++k) g[k] = -c.res_grad[k] * c.jac[k];
@@ -100,6 +117,15 @@ __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers&
         double g[LBFGS_MAXN];
         for (int k = 0; k < n; ++k) g[k] = ok ? -c.res_grad[k] * c.jac[k] : 0.0;
         c.S.feed(ok, -c.res_ll, g, lo);
+    }
+    if (c.phase == PH_NM) {                               // Nelder-Mead finished: report through the common fields
+        c.S.f = c.NM.fbest;
+        lb_copy(c.S.x, c.NM.xbest, n);
+        c.S.iters = c.NM.iters;
+        c.S.nfev = fp.P + c.NM.nfev;
+        c.S.status = c.NM.status;
+        c.phase = PH_DONE;
+        return;
     }
     if (c.S.status != LbfgsState::RUNNING) { c.phase = PH_DONE; return; }
     c.phase = PH_LBFGS;

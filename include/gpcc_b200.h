@@ -34,6 +34,7 @@ enum { GPCC_KERNEL_OU = 0, GPCC_KERNEL_RBF = 1, GPCC_KERNEL_MATERN32 = 2, GPCC_K
 /* Parameter transforms of src/gpccfixdelay_marginaliseb.jl:112-114 (MiscUtil.makepositive /
  * transformbetween, un-vendored): id 0 = softplus + 1e-8 floor, rhomin+(rhomax-rhomin)*logistic.   */
 enum { GPCC_TRANSFORM_SOFTPLUS_LOGISTIC = 0 };
+enum { GPCC_OPT_LBFGS = 0, GPCC_OPT_NELDERMEAD = 1 };
 
 typedef struct gpcc_ctx gpcc_ctx;
 typedef struct gpcc_problem gpcc_problem;
@@ -51,6 +52,10 @@ typedef struct gpcc_fit_options {
     int    transform_id;    /* GPCC_TRANSFORM_*                                                    */
     int    theta0_per_candidate; /* 0: theta0 is [P][L+1] shared by all candidates (the reference's
                                     seed=1 behaviour, :62); 1: theta0 is [M][P][L+1]               */
+    int    optimizer;       /* GPCC_OPT_LBFGS (default) or GPCC_OPT_NELDERMEAD: the reference's own optimiser
+                               (:205-211, g_tol = nm_gtol), on the device, for basin-for-basin comparisons;
+                               fused small-N path only (N <= 199)                                  */
+    double nm_gtol;         /* Optim.Options(g_tol = 1e-6) (:205): simplex spread at which Nelder-Mead stops */
 } gpcc_fit_options;
 
 /* Per-stage device timings of the most recent call, measured with CUDA events on the library's own

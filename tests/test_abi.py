@@ -70,6 +70,7 @@ def test_fit_options_default_matches_reference_constants():
     assert lib.gpcc_fit_options_default(C.byref(o)) == 0
     assert o.max_iter == 1000 and o.rhomin == 0.1 and o.alpha_floor == 1e-8       # :46, :112
     assert o.history == 8 and o.transform_id == 0 and o.theta0_per_candidate == 0
+    assert o.optimizer == 0 and o.nm_gtol == 1e-6                                   # L-BFGS by default; g_tol of :205 for the NM option
     assert lib.gpcc_fit_options_default(None) != 0
 
 

@@ -74,7 +74,7 @@ def test_one_process_per_gpu_library_allgather(ctx, tmp_path):
     env = dict(os.environ, GPCC_ROOT=root, WORLD_SIZE="2", IDFILE=str(tmp_path / "nccl_id"), OUTFILE=str(tmp_path / "out"))
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
              for r in range(2)]
-    outs = [q.communicate(timeout=600) for q in procs]
+    outs = [q.communicate(timeout=150) for q in procs]
     for q, (o, e) in zip(procs, outs):
         assert q.returncode == 0, e[-3000:]
     g = load_golden("fit_cfg1_cfg2")

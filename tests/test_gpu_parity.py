@@ -252,6 +252,48 @@ def test_restarts_and_per_candidate_starts(ctx):
     assert capped["info"][0] == 1 and capped["iters"][0] == 2 and capped["loglikel"][0] < float(g["loglikel"])
 
 
+# ---- the reference's own optimiser on the device (nm.h): basin-for-basin comparison ---------------------------------------
+def test_device_nelder_mead_matches_oracle_nelder_mead(ctx):
+    """optimizer="neldermead": Optim's adaptive Nelder-Mead (:205-211) as a device state machine on forward-only evaluations,
+    against the oracle's restatement of the same algorithm from the same start points.  NM stops when the simplex spread is
+    below g_tol = 1e-6, so two runs whose comparisons flip on the last bits end up to ~1e-5 apart."""
+    g = load_golden("fit_cfg1_cfg2")
+    p = Problem(g["tb"], g["yb"], g["sb"], "matern32", ctx)
+    delays = np.stack([np.zeros_like(g["cands"]), g["cands"]], 1)
+    r = p.grid_posterior(delays, g["theta0"], iterations=1000, rhomin=0.1, rhomax=300.0, optimizer="neldermead")
+    gap = np.abs(r["loglikel"] - g["ll_grid_nm"])
+    print("cfg2 device NM vs oracle NM: median gap %.1e, max %.1e, beyond 1e-4: %d of %d; mean evaluations %.0f"
+          % (np.median(gap), gap.max(), np.sum(gap > 1e-4), len(gap), r["nfev"].mean()))
+    assert np.median(gap) < 1e-6 and np.max(gap[g["post_flat"] > 1e-12]) < 3e-5
+    assert np.max(np.abs(r["posterior"] - oracle.getprobabilities(g["ll_grid_nm"]))) < POST_ATOL
+    assert np.max(np.abs(r["posterior"] - g["post_flat"])) < POST_ATOL                 # and the same posterior as the L-BFGS fit
+    ll, _, _ = gpcc_b200.gpcc(g["tb"], g["yb"], g["sb"], kernel="matern32", delays=g["truedelays"], iterations=1000, rhomax=300,
+                              theta0=g["theta0"], ctx=ctx, verbose=False, optimizer="neldermead")
+    assert abs(ll - float(g["loglikel_nm"])) < 3e-5 and ll <= float(g["loglikel"]) + 1e-9
+    capped = p.fit_batch(delays[:4], g["theta0"], iterations=3, rhomin=0.1, rhomax=300.0, optimizer="neldermead")
+    assert np.all(capped["info"] == 1) and np.all(capped["iters"] == 3)
+    big = Problem(*gpcc_b200.synthetic_bands([120, 110], seed=9)[:3], "matern32", ctx)
+    with pytest.raises(gpcc_b200.GpccError):                                             # tiled path: L-BFGS only
+        big.fit_batch([[0.0, 1.0]], g["theta0"], iterations=10, rhomin=0.1, rhomax=300.0, optimizer="neldermead")
+
+
+def test_device_nelder_mead_full_cfg3_grid_against_oracle(ctx):
+    """All 10 201 candidates of BASELINE config 3 with the reference's optimiser on both sides
+    (tests/golden/fit_cfg3_full_nm.npz: the oracle's Nelder-Mead, 16 CPU-minutes; here ~1.5 s)."""
+    g = load_golden("fit_cfg3_full_nm")
+    t, y, s, d = oracle.simulatethreelightcurves()
+    p = Problem(t, y, s, "matern32", ctx)
+    r = p.grid_posterior(g["delays"], g["theta0"], iterations=1000, rhomin=0.1, rhomax=300.0, optimizer="neldermead")
+    gap = np.abs(r["loglikel"] - g["ll"])
+    mass = g["post"] > 1e-12
+    print("cfg3 full grid, NM vs NM: %d candidates with mass, max gap there %.1e; same basin (gap < 1e-4) on %d of %d candidates; "
+          "mean evaluations %.0f (oracle %.0f)" % (mass.sum(), gap[mass].max(), np.sum(gap < 1e-4), len(gap), r["nfev"].mean(), g["nfev"].mean()))
+    assert np.max(gap[mass]) < 3e-5
+    assert np.max(np.abs(r["posterior"] - g["post"])) < POST_ATOL
+    assert np.mean(gap < 1e-4) > 0.9                    # basin for basin: the two Nelder-Mead runs agree on (nearly) every candidate
+    assert abs(r["nfev"].mean() - g["nfev"].mean()) < 0.1 * g["nfev"].mean()
+
+
 # ---- large-N path (tile layout in HBM, DMMA trailing updates), BASELINE configs 4/5 --------------------------
 @pytest.mark.parametrize("nper,kernel", [([100, 90, 70], "matern32"), ([256, 256, 256], "matern52"), ([300, 212], "OU"),
                                          ([201], "rbf"), ([64, 64, 64, 64], "matern32")])
