@@ -330,6 +330,43 @@ __device__ __forceinline__ void eval_one(const DevProblem& p, int T, double* sme
             for (int c = 0; c < 8; ++c) A[r][c] = 0.0;
     } else
 #endif
+#ifdef GPCC_ROLL_ASSEMBLY   // measured slower (all 64 accumulators live from the first row on: spills); kept for the record
+    {
+        // The row loop is ROLLED and the finished row lands in its registers through a switch with static indices: one copy of
+        // the eight kernel evaluations (8 x FP64 exp) instead of 64.  The profile of the fully unrolled form showed these
+        // phases bound by instruction fetch (64 KB of straight-line code per phase, executed once per evaluation, with two
+        // CTAs per SM in different phases: stall_no_inst was 45 % of their samples and 18 % of the whole kernel).
+        double tc[8], ac[8], rc[8];
+        int bc[8];
+        load8(tsh, tj, tc);
+        load8(av, tj, ac);
+        load8(abuf, tj, rc);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bc[c] = bandv[tj * 8 + c];
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+            const int i = ti * 8 + r;
+            const int ci = cidx(i);
+            const double tr = tsh[ci], ar = av[ci], sbr = sbv[ci], dr = dadd[ci];
+            const int br = bandv[i];
+            double val[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = tj * 8 + c;
+                const double kv = kern_value<KID>(tr - tc[c], kp);
+                double v = (ar * ac[c]) * kv;            // scale[l]*scale[m]*kernel  (delayedCovariance.jl:27)
+                if (i == j) v += dr;                     // + Sobs                   (gpccfixdelay_marginaliseb.jl:135)
+                if (br == bc[c]) v += sbr;               // + B = Q Sigma_b Q'
+                if (i == N) v = rc[c];                   // border row: r = Y - bbar (corner = 0)
+                if (i > N && i == j) v = 1.0;            // padding
+                val[c] = v;
+            }
+#define GPCC_ROW_IN(R) case R: _Pragma("unroll") for (int c = 0; c < 8; ++c) A[R][c] = val[c]; break;
+            switch (r) { GPCC_ROW_IN(0) GPCC_ROW_IN(1) GPCC_ROW_IN(2) GPCC_ROW_IN(3) GPCC_ROW_IN(4) GPCC_ROW_IN(5) GPCC_ROW_IN(6) default: _Pragma("unroll") for (int c = 0; c < 8; ++c) A[7][c] = val[c]; break; }
+#undef GPCC_ROW_IN
+        }
+    }
+#else
     {
         double tc[8], ac[8], rc[8];
         int bc[8];
@@ -357,6 +394,7 @@ __device__ __forceinline__ void eval_one(const DevProblem& p, int T, double* sme
             }
         }
     }
+#endif
     __syncthreads();   // everyone has read abuf/tsh before cbuf traffic starts (abuf is reused later)
 
     // ---- publish column 0, then N sweep steps ----------------------------------------------------
@@ -381,27 +419,16 @@ __device__ __forceinline__ void eval_one(const DevProblem& p, int T, double* sme
 #else
     publish_lean<0>(A, ti, tj, 0, cbuf, pbuf, piv, fast_rcp(A[0][0]), fwd);
     __syncthreads();
-    {
-        const int full = N >> 3, rem = N & 7;   // the last step also publishes "column N" (the border row): never read, harmless
-        for (int tk = 0; tk < full; ++tk) {
-            const int k0 = tk * 8;
-            sweep_step_lean<0>(A, ti, tj, tk, k0 + 0, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<1>(A, ti, tj, tk, k0 + 1, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<2>(A, ti, tj, tk, k0 + 2, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<3>(A, ti, tj, tk, k0 + 3, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<4>(A, ti, tj, tk, k0 + 4, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<5>(A, ti, tj, tk, k0 + 5, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<6>(A, ti, tj, tk, k0 + 6, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-            sweep_step_lean<7>(A, ti, tj, tk, k0 + 7, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        }
-        const int tk = full, k0 = full * 8;
-        if (rem > 0) sweep_step_lean<0>(A, ti, tj, tk, k0 + 0, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        if (rem > 1) sweep_step_lean<1>(A, ti, tj, tk, k0 + 1, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        if (rem > 2) sweep_step_lean<2>(A, ti, tj, tk, k0 + 2, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        if (rem > 3) sweep_step_lean<3>(A, ti, tj, tk, k0 + 3, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        if (rem > 4) sweep_step_lean<4>(A, ti, tj, tk, k0 + 4, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        if (rem > 5) sweep_step_lean<5>(A, ti, tj, tk, k0 + 5, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
-        if (rem > 6) sweep_step_lean<6>(A, ti, tj, tk, k0 + 6, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+    for (int tk = 0; 8 * tk < N; ++tk) {   // one copy of the eight specialised steps; the guards only matter in the last tile
+        const int k0 = tk * 8;               // (the last step also publishes "column N", the border row: never read, harmless)
+        sweep_step_lean<0>(A, ti, tj, tk, k0 + 0, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 1 < N) sweep_step_lean<1>(A, ti, tj, tk, k0 + 1, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 2 < N) sweep_step_lean<2>(A, ti, tj, tk, k0 + 2, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 3 < N) sweep_step_lean<3>(A, ti, tj, tk, k0 + 3, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 4 < N) sweep_step_lean<4>(A, ti, tj, tk, k0 + 4, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 5 < N) sweep_step_lean<5>(A, ti, tj, tk, k0 + 5, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 6 < N) sweep_step_lean<6>(A, ti, tj, tk, k0 + 6, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
+        if (k0 + 7 < N) sweep_step_lean<7>(A, ti, tj, tk, k0 + 7, cbuf, pbuf, piv, fwd GPCC_PROF_ARG);
     }
 #endif
 
@@ -457,6 +484,58 @@ __device__ __forceinline__ void eval_one(const DevProblem& p, int T, double* sme
     }
     __syncthreads();
 
+#ifdef GPCC_ROLL_GRADIENT
+    double es = 0.0;
+    const bool diag_tile = (ti == tj);
+    double* myrow = part + (ti * T + tj) * 8;       // row sums of this tile, [8]
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {           // four columns at a time: limits the live column data
+        double tc[4], ac[4], wc[4], cols[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int cj = cidx(tj * 8 + half * 4 + cc);
+            tc[cc] = tsh[cj]; ac[cc] = av[cj]; wc[cc] = abuf[cj]; cols[cc] = 0.0;
+        }
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {                // rolled, like the assembly: one copy of the four kernel evaluations
+            const int ci = cidx(ti * 8 + r);
+            const double tr = tsh[ci], ar = av[ci], wr = abuf[ci];
+            double ain[4];
+#define GPCC_ROW_OUT(R) case R: _Pragma("unroll") for (int cc = 0; cc < 4; ++cc) ain[cc] = A[R][half * 4 + cc]; break;
+            switch (r) { GPCC_ROW_OUT(0) GPCC_ROW_OUT(1) GPCC_ROW_OUT(2) GPCC_ROW_OUT(3) GPCC_ROW_OUT(4) GPCC_ROW_OUT(5) GPCC_ROW_OUT(6) default: _Pragma("unroll") for (int cc = 0; cc < 4; ++cc) ain[cc] = A[7][half * 4 + cc]; break; }
+#undef GPCC_ROW_OUT
+            double rsum = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = half * 4 + cc;
+                const double W = fma(wr, wc[cc], ain[cc]);        // a_i a_j - (K~^-1)_ij
+                double kv, dkv;
+                kern_value_drho<KID>(tr - tc[cc], kp, kv, dkv);
+                const double aa = ar * ac[cc];                   // 0 on padding / border rows
+                double ct = W * (aa * kv);
+                double et = W * (aa * dkv);
+                if (diag_tile) {
+                    if (r == c) { rsum += ct; ct = 0.0; et = 0.0; }      // diagonal counted once, dk(0)=0
+                    else if (r < c) { ct = 0.0; et = 0.0; }              // upper part of the tile is unused
+                }
+                rsum += ct;
+                cols[cc] += ct;
+                es += et;
+            }
+            if (active) { if (half == 0) myrow[r] = rsum; else myrow[r] += rsum; }
+        }
+        if (active && !diag_tile) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) part[(tj * T + ti) * 8 + half * 4 + cc] = cols[cc];
+        }
+        if (active && diag_tile) {
+            // fold the column sums of the strictly-lower part into the same slots as the row sums (the slots belong to this
+            // thread alone, so the later "+=" of the second half simply adds on top)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) myrow[half * 4 + cc] += cols[cc];
+        }
+    }
+#else
     double rows[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) rows[r] = 0.0;
@@ -510,6 +589,7 @@ __device__ __forceinline__ void eval_one(const DevProblem& p, int T, double* sme
 #pragma unroll
         for (int r = 0; r < 8; ++r) part[(ti * T + tj) * 8 + r] = rows[r];
     }
+#endif
     es = block_sum(active ? es : 0.0, red, tid, nthreads);   // (contains the __syncthreads that orders `part`)
 
     // s_i = sum_j W_ij K_ij (full row);  dlogL/dalpha_p = (1/alpha_p) sum_{i in band p} s_i

@@ -12,6 +12,10 @@
 // host synchronisations per fitted grid, the straggler tail of the batched rounds (a round ends when its slowest
 // candidate ends; here a slow candidate only occupies its own CTA) and the host threads that contend when 8 ranks share
 // one box.  Results do not depend on the schedule: candidates never interact.
+// The gradient phase is compiled in its rolled form here (one copy of the kernel evaluations instead of 32): the CTAs of the
+// persistent kernel drift apart, two co-resident CTAs are usually in different phases, and the smaller instruction footprint
+// measured 2 % faster (profiles/README.md); in the batch kernel, whose CTAs run in step, it is neutral.
+#define GPCC_ROLL_GRADIENT
 #include "small_eval.cuh"
 #include "lbfgs.h"
 #include "nm.h"
@@ -29,6 +33,7 @@ struct FitCtl {                 // per-CTA control block in shared memory
     double alpha[MAX_BANDS];    // constrained parameters of the evaluation in flight
     double rho;
     double jac[LBFGS_MAXN];     // d(alpha, rho)/d theta at the evaluation in flight
+    double theta_next[LBFGS_MAXN];   // unconstrained parameters of the next evaluation (unpacked by L+1 threads)
     double theta_best[LBFGS_MAXN];
     double grad_best[LBFGS_MAXN];
     double res_ll;
@@ -43,18 +48,26 @@ enum { PH_SCREEN = 0, PH_START = 1, PH_LBFGS = 2, PH_DONE = 3, PH_NM = 4 };
 __device__ __forceinline__ double softplus(double x) { return x > 0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
 __device__ __forceinline__ double logistic(double x) { return 0.5 * (1.0 + tanh(0.5 * x)); }
 
-// unpack (gpccfixdelay_marginaliseb.jl:112-126): alpha = makepositive(theta_l) + floor, rho = transformbetween(theta_L+1)
-__device__ void unpack_to_ctl(FitCtl& c, const double* theta, int L, const FitParams& fp) {
-    for (int l = 0; l < L; ++l) {
-        c.alpha[l] = softplus(theta[l]) + fp.alpha_floor;
-        c.jac[l] = logistic(theta[l]);
+// unpack (gpccfixdelay_marginaliseb.jl:112-126): alpha = makepositive(theta_l) + floor, rho = transformbetween(theta_L+1).
+// One thread per parameter: the FP64 exp / log1p / tanh chains of the L+1 transforms run side by side instead of one after
+// the other on thread 0 (the profile showed the other five warps waiting ~9 % of the kernel time for that thread).
+__device__ __forceinline__ void unpack_to_ctl(FitCtl& c, const double* theta, int, const FitParams&) {
+    for (int k = 0; k < c.S.n; ++k) c.theta_next[k] = theta[k];
+}
+__device__ __forceinline__ void unpack_parallel(FitCtl& c, int tid, int L, const FitParams& fp) {
+    if (tid < L) {
+        c.alpha[tid] = softplus(c.theta_next[tid]) + fp.alpha_floor;
+        c.jac[tid] = logistic(c.theta_next[tid]);
+    } else if (tid == L) {
+        const double s = logistic(c.theta_next[L]);
+        c.rho = fp.rhomin + (fp.rhomax - fp.rhomin) * s;
+        c.jac[L] = (fp.rhomax - fp.rhomin) * s * (1.0 - s);
     }
-    const double s = logistic(theta[L]);
-    c.rho = fp.rhomin + (fp.rhomax - fp.rhomin) * s;
-    c.jac[L] = (fp.rhomax - fp.rhomin) * s * (1.0 - s);
 }
 
 // Thread 0: consume the result of the evaluation that just finished (if any) and set up the next one, or finish.
+// OPT is a template parameter so that the Nelder-Mead code does not weigh on the registers of the default (L-BFGS) kernel.
+template <int OPT>
 __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers& fb, const LbfgsOptions& lo) {
     const int n = L + 1;
     const double* th0 = fb.theta0 + (fp.theta0_per_candidate ? (size_t)c.cand * fp.P * n : 0);
@@ -86,7 +99,7 @@ __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers&
             c.S.f = c.bestf; c.S.status = LbfgsState::ITER_CAP; c.phase = PH_DONE;
             return;
         }
-        if (fp.optimizer == 1) {                          // the reference's Nelder-Mead (:205-211): forward-only evaluations
+        if (OPT == 1) {                                   // the reference's Nelder-Mead (:205-211): forward-only evaluations
             c.NM.start(n, c.theta_best, c.bestf, fp.max_iter, fp.nm_gtol);
             c.phase = PH_NM;
             if (c.NM.phase != NmState::DONE) {
@@ -100,8 +113,8 @@ __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers&
             c.phase = PH_START;
             return;
         }
-        if (fp.optimizer != 1) c.S.start(n, c.theta_best, c.bestf, c.grad_best, lo);
-    } else if (c.phase == PH_NM) {                        // result at NM.xt
+        if (OPT != 1) c.S.start(n, c.theta_best, c.bestf, c.grad_best, lo);
+    } else if (OPT == 1 && c.phase == PH_NM) {                        // result at NM.xt
         c.NM.feed(c.res_info == 0 && lb_finite(c.res_ll), -c.res_ll, fp.max_iter, fp.nm_gtol);
         if (c.NM.phase != NmState::DONE) {
             unpack_to_ctl(c, c.NM.xt, L, fp);
@@ -118,7 +131,7 @@ __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers&
         for (int k = 0; k < n; ++k) g[k] = ok ? -c.res_grad[k] * c.jac[k] : 0.0;
         c.S.feed(ok, -c.res_ll, g, lo);
     }
-    if (c.phase == PH_NM) {                               // Nelder-Mead finished: report through the common fields
+    if (OPT == 1 && c.phase == PH_NM) {                   // Nelder-Mead finished: report through the common fields
         c.S.f = c.NM.fbest;
         lb_copy(c.S.x, c.NM.xbest, n);
         c.S.iters = c.NM.iters;
@@ -133,7 +146,7 @@ __device__ void advance(FitCtl& c, int L, const FitParams& fp, const FitBuffers&
     c.want_grad = 1; c.fwd = 0; ++c.n_grad;
 }
 
-template <int KID, int MAXTHREADS, int MINBLOCKS>
+template <int KID, int MAXTHREADS, int MINBLOCKS, int OPT>
 __global__ void __launch_bounds__(MAXTHREADS, MINBLOCKS)
 small_fit_kernel(DevProblem p, FitParams fp, FitBuffers fb, int T, int ctl_offset_doubles) {
     extern __shared__ __align__(16) double smem[];
@@ -151,7 +164,7 @@ small_fit_kernel(DevProblem p, FitParams fp, FitBuffers fb, int T, int ctl_offse
         if (tid == 0) {
             const unsigned long long qpos = atomicAdd(fb.counters, 1ULL);
             c.cand = qpos < (unsigned long long)fp.M ? fb.order[qpos] : fp.M;
-            c.phase = PH_SCREEN; c.j = 0; c.best = -1; c.bestf = lb_inf();
+            c.phase = PH_SCREEN; c.j = 0; c.best = -1; c.bestf = lb_inf(); c.S.n = n;
             c.n_grad = 0; c.n_fwd = 0;
         }
         __syncthreads();
@@ -159,9 +172,11 @@ small_fit_kernel(DevProblem p, FitParams fp, FitBuffers fb, int T, int ctl_offse
         if (cand >= fp.M) break;
         if (tid < L) c.delays[tid] = fb.delays[(size_t)cand * L + tid];
         for (;;) {
-            if (tid == 0) advance(c, L, fp, fb, lo);
+            if (tid == 0) advance<OPT>(c, L, fp, fb, lo);
             __syncthreads();
             if (c.phase == PH_DONE) break;
+            if (tid <= L) unpack_parallel(c, tid, L, fp);
+            __syncthreads();
             eval_one<KID>(p, T, smem, c.delays, c.alpha, c.rho, c.want_grad != 0, c.fwd != 0, &c.res_ll, c.res_grad, &c.res_info);
             __syncthreads();
         }
@@ -184,9 +199,9 @@ small_fit_kernel(DevProblem p, FitParams fp, FitBuffers fb, int T, int ctl_offse
     }
 }
 
-template <int KID, int MT, int MB>
-cudaError_t go(const DevProblem& p, const FitParams& fp, const FitBuffers& fb, int T, int threads, int maxT, int nsm, cudaStream_t s) {
-    auto kfn = small_fit_kernel<KID, MT, MB>;
+template <int KID, int MT, int MB, int OPT>
+cudaError_t go2(const DevProblem& p, const FitParams& fp, const FitBuffers& fb, int T, int threads, int maxT, int nsm, cudaStream_t s) {
+    auto kfn = small_fit_kernel<KID, MT, MB, OPT>;
     const size_t ev = (eval_smem_bytes(T, 1) + 15) / 16 * 16;
     const size_t ev_max = (eval_smem_bytes(maxT, 1) + 15) / 16 * 16;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ev_max + sizeof(FitCtl)));
@@ -198,6 +213,12 @@ cudaError_t go(const DevProblem& p, const FitParams& fp, const FitBuffers& fb, i
     const int grid = (int)std::min<long long>(fp.M, (long long)nsm * per_sm);
     kfn<<<grid, threads, ev + sizeof(FitCtl), s>>>(p, fp, fb, T, (int)(ev / 8));
     return cudaGetLastError();
+}
+
+template <int KID, int MT, int MB>
+cudaError_t go(const DevProblem& p, const FitParams& fp, const FitBuffers& fb, int T, int threads, int maxT, int nsm, cudaStream_t s) {
+    if (fp.optimizer == 1) return go2<KID, MT, MB, 1>(p, fp, fb, T, threads, maxT, nsm, s);
+    return go2<KID, MT, MB, 0>(p, fp, fb, T, threads, maxT, nsm, s);
 }
 
 template <int KID>

@@ -23,9 +23,11 @@ matern52(xi, xj; ρ = 1.0) = (r = abs(xi - xj); (1 + sqrt(5) * r / ρ + 5 * r^2 
 kernelid(k) = k === OU ? 0 : k === rbf ? 1 : k === matern32 ? 2 : k === matern52 ? 3 :
     error("GPCC_B200: unsupported kernel (expected OU, rbf, matern32 or matern52)")
 
-struct FitOptions          # mirrors gpcc_fit_options
+struct FitOptions          # mirrors gpcc_fit_options (include/gpcc_b200.h), field for field
     max_iter::Cint; rhomin::Cdouble; rhomax::Cdouble; alpha_floor::Cdouble; gtol::Cdouble; ftol::Cdouble
     history::Cint; transform_id::Cint; theta0_per_candidate::Cint
+    optimizer::Cint          # 0 = L-BFGS on the analytic gradient (default), 1 = Nelder-Mead on the device (the reference's, :205-211)
+    nm_gtol::Cdouble         # Optim.Options(g_tol = 1e-6) (:205)
 end
 
 lasterror() = unsafe_string(ccall((:gpcc_last_error, LIB), Cstring, ()))
@@ -39,6 +41,15 @@ mutable struct Context
         c = new(r[]); finalizer(c -> ccall((:gpcc_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), c); c
     end
 end
+# One Julia process per GPU (`addprocs`, README.md:185-189): worker 1 draws the id with `communiqueid()`, the script sends the
+# 128 bytes to the other workers (e.g. through `remotecall`), every worker calls `comminitrank!(ctx, nworkers, rank, id)`;
+# from then on `gpccgrid` shards the grid over the workers' GPUs and all-gathers the results with NCCL.
+function communiqueid()
+    id = zeros(UInt8, 128)
+    check(ccall((:gpcc_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id
+end
+comminitrank!(c::Context, world::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:gpcc_ctx_comm_init_rank, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), c.h, world, rank, id))
 const DEFAULT = Ref{Union{Nothing, Context}}(nothing)
 defaultctx() = (DEFAULT[] === nothing && (DEFAULT[] = Context(parse(Int, get(ENV, "GPCC_B200_NDEV", "1")))); DEFAULT[])
 
@@ -77,7 +88,18 @@ function startpoints(yarray, seed, numberofrestarts, initialrandom, ρmin, ρmax
     θ0, initialρ
 end
 
-options(iterations, ρmin, ρmax; percandidate = false) = FitOptions(iterations, ρmin, ρmax, 1e-8, 1e-7, 1e-13, 8, 0, percandidate ? 1 : 0)
+options(iterations, ρmin, ρmax; percandidate = false, neldermead = false) =
+    FitOptions(iterations, ρmin, ρmax, 1e-8, 1e-7, 1e-13, 8, 0, percandidate ? 1 : 0, neldermead ? 1 : 0, 1e-6)
+
+# The state the reference's `pred` closures capture (:235-252): ONE factorisation per fitted (delays, alpha, rho), kept on the GPU.
+mutable struct FitState
+    h::Ptr{Cvoid}; p::Problem
+    function FitState(p::Problem, d::Vector{Float64}, α::Vector{Float64}, ρ::Float64)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve d α check(ccall((:gpcc_fit_state_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ref{Ptr{Cvoid}}), p.h, d, α, ρ, r))
+        s = new(r[], p); finalizer(s -> ccall((:gpcc_fit_state_destroy, LIB), Cint, (Ptr{Cvoid},), s.h), s); s   # any destroy order is safe
+    end
+end
 
 function fitbatch(p::Problem, delays::Matrix{Float64}, θ0, opt::FitOptions)     # delays: L x M (column per candidate)
     L, M = size(delays); P = size(θ0, 2)
@@ -94,7 +116,7 @@ end
 Same contract as GPCC.gpcc (gpccfixdelay_marginaliseb.jl:46-53, 351).
 """
 function gpcc(tarray, yarray, stdarray; kernel = kernel, delays = delays, iterations = iterations, seed = 1,
-              numberofrestarts = 1, initialrandom = 5, rhomin = 0.1, rhomax = rhomax)
+              numberofrestarts = 1, initialrandom = 5, rhomin = 0.1, rhomax = rhomax, neldermead = false)
     p = Problem(defaultctx(), tarray, yarray, stdarray, kernel); L = p.L
     @assert L == length(delays)
     Σb = 100 .* map(var, yarray)
@@ -105,33 +127,34 @@ function gpcc(tarray, yarray, stdarray; kernel = kernel, delays = delays, iterat
     θ0, initialρ = startpoints(yarray, seed, numberofrestarts, initialrandom, rhomin, rhomax)
     @printf("\n\tInitial ρ values are:\n"); map(x -> @printf("\t%f\n", x), initialρ)
     τ = repeat(Float64.(delays), 1, numberofrestarts)                                # one "candidate" per restart (:222-226)
-    ll, αs, ρs, _ = fitbatch(p, τ, θ0, options(iterations, rhomin, rhomax; percandidate = true))
+    ll, αs, ρs, _ = fitbatch(p, τ, θ0, options(iterations, rhomin, rhomax; percandidate = true, neldermead = neldermead))
     b = argmax(ll); α = αs[:, b]; ρ = ρs[b]
     @printf("\n\tOverall minimum is %f\n", -ll[b]); @show α, ρ                        # :228, :235
     d = Float64.(delays); μ = zeros(L); Σ = zeros(L, L)
-    GC.@preserve d α μ Σ check(ccall((:gpcc_postb, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}), p.h, d, α, ρ, μ, Σ))
+    st = FitState(p, d, α, ρ)                                                        # K, KSobsB (:237-241): factorised once
+    GC.@preserve μ Σ check(ccall((:gpcc_fit_state_postb, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), st.h, μ, Σ))
     postb = MvNormal(μ, Symmetric(Σ))                                                # :252
 
     function predictTest(ttest::Union{Array{Array{Float64, 1}, 1}, Array{T} where T <: AbstractRange{S} where S <: Real})   # :259-289
         nt = Cint.(length.(ttest)); tt = Float64.(reduce(vcat, collect.(ttest))); NT = length(tt)
         μp = zeros(NT); Σp = zeros(NT, NT)
-        GC.@preserve d α nt tt μp Σp check(ccall((:gpcc_predict, LIB), Cint,
-            (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), p.h, d, α, ρ, nt, tt, μp, C_NULL, Σp))
+        GC.@preserve nt tt μp Σp check(ccall((:gpcc_fit_state_predict, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), st.h, nt, tt, μp, C_NULL, Σp))
         μp, Σp
     end
     function predictTest(ttest::Union{AbstractRange{Float64}, Array{Float64, 1}})                                          # :293-307
         Nt = length(ttest); nt = fill(Cint(Nt), L); tt = repeat(Float64.(collect(ttest)), L); μp = zeros(L * Nt); σp = zeros(L * Nt)
-        GC.@preserve d α nt tt μp σp check(ccall((:gpcc_predict, LIB), Cint,
-            (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), p.h, d, α, ρ, nt, tt, μp, σp, C_NULL))
+        GC.@preserve nt tt μp σp check(ccall((:gpcc_fit_state_predict, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), st.h, nt, tt, μp, σp, C_NULL))
         [μp[idx] for idx in Iterators.partition(1:L*Nt, Nt)], [σp[idx] for idx in Iterators.partition(1:L*Nt, Nt)]
     end
     function predictTest(ttest::Array{Array{Float64, 1}, 1}, ytest::Array{Array{Float64, 1}, 1}, σtest::Array{Array{Float64, 1}, 1})   # :311-343
-        nt = Cint.(length.(ttest)); tt = reduce(vcat, ttest); yt = reduce(vcat, ytest); st = reduce(vcat, σtest)
+        nt = Cint.(length.(ttest)); tt = reduce(vcat, ttest); yt = reduce(vcat, ytest); σt = reduce(vcat, σtest)
         ll_ = Ref{Cdouble}(0.0); info = Ref{Cint}(0)
-        GC.@preserve d α nt tt yt st check(ccall((:gpcc_predict_loglik, LIB), Cint,
-            (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{Cint}), p.h, d, α, ρ, nt, tt, yt, st, ll_, info))
+        GC.@preserve nt tt yt σt check(ccall((:gpcc_fit_state_predict_loglik, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{Cint}), st.h, nt, tt, yt, σt, ll_, info))
         if info[] != 0      # PosDefException branch (:327-333): repair on the host exactly as the reference does
-            μp, Σp = predictTest(ttest); Σp = Σp + Diagonal(st .^ 2)
+            μp, Σp = predictTest(ttest); Σp = Σp + Diagonal(σt .^ 2)
             return logpdf(MvNormal(μp, MiscUtil.nearestposdef(MiscUtil.makematrixsymmetric(Σp); minimumeigenvalue = 1e-6)), yt)
         end
         ll_[]
