@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <vector>
+#include <cstdio>
 
 namespace gpcc {
 namespace {
@@ -256,21 +257,89 @@ __global__ void __launch_bounds__(256) pivot_kernel(LargeArgs a, int k) {
     if (tid < BT) rk[tid] = a.rvec[(size_t)m * a.Np + k * BT + tid];
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    // ---- right-looking Cholesky: 2 barriers per column, 16x16 thread grid over the trailing block ----
-    for (int j = 0; j < BT; ++j) {
-        __syncthreads();                                   // trailing update of column j-1 is complete
-        const double d = SE(S, j, j);
-        if (!(d > 0.0) && tid == 0 && s_bad == 0) s_bad = j + 1;
-        const double sq = sqrt(d), inv = 1.0 / sq;
-        if (tid > j && tid < BT) SE(S, tid, j) *= inv;    // nobody reads column j (below the diagonal) in this phase
-        __syncthreads();
-        if (tid == j) { SE(S, j, j) = sq; ldiag[j] = sq; } // the trailing phase never reads S(j,j)
-        for (int i = j + 1 + ty; i < BT; i += 16) {
-            const double lij = SE(S, i, j);
-            for (int c = j + 1 + tx; c <= i; c += 16) SE(S, i, c) = fma(-lij, SE(S, c, j), SE(S, i, c));
+#ifdef GPCC_PIVOT_PROF
+    long long tp0 = clock64();
+#endif
+    // ---- blocked Cholesky, panels of NB = 16 columns -----------------------------------------------------------------------
+    // Inside a panel the columns are formed LEFT-LOOKING, one thread per row: column j first receives the updates of the
+    // panel columns before it (a dot product of <= 15 terms per row; every thread also forms the pivot itself, with the same
+    // operations, so that no broadcast is needed), is scaled, and ONE barrier publishes it.  Behind the panel: one rank-16
+    // update of everything to its right, 4 x 4 register blocks per thread, 16 FMAs per 8 shared-memory loads.
+    // History (profiles/README.md, round 2): the unblocked form (rank-1 update of the whole trailing block after every column,
+    // 2 barriers per column) took ~330 us of a 536 us kernel that is the critical path of every block step; a right-looking
+    // panel 79 us; this form is measured there as well.
+    constexpr int NB = 16;
+    for (int j0 = 0; j0 < BT; j0 += NB) {
+        for (int j = j0; j < j0 + NB; ++j) {
+            if (tid >= j && tid < BT) {
+                const int i = tid;
+                // all loads first (predicated off beyond column j), then two short FMA chains per sum: the loop form
+                // (load, load, fma, fma per term) ran at one shared-memory round trip per term
+                double lik[NB], ljk[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const bool on = j0 + q < j;
+                    lik[q] = on ? SE(S, i, j0 + q) : 0.0;
+                    ljk[q] = on ? SE(S, j, j0 + q) : 0.0;
+                }
+                double s0 = SE(S, i, j), s1 = 0.0, d0 = SE(S, j, j), d1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < NB; q += 2) {
+                    s0 = fma(-lik[q], ljk[q], s0);
+                    s1 = fma(-lik[q + 1], ljk[q + 1], s1);
+                    d0 = fma(-ljk[q], ljk[q], d0);
+                    d1 = fma(-ljk[q + 1], ljk[q + 1], d1);
+                }
+                const double sij = s0 + s1, sjj = d0 + d1;
+                const double rs = rsqrt(sjj);                   // NaN for a non-positive pivot, like sqrt
+                const double sq = sjj * rs;
+                if (i == j) {                                   // S(j,j) itself is written after the panel: the other rows still read it
+                    ldiag[j] = sq;
+                    if (!(sjj > 0.0) && s_bad == 0) s_bad = j + 1;
+                } else {
+                    SE(S, i, j) = sij * rs;
+                }
+            }
+            __syncthreads();
         }
+        if (tid >= j0 && tid < j0 + NB) SE(S, tid, tid) = ldiag[tid];
+        __syncthreads();
+        const int r0 = j0 + NB;                                // trailing block starts here
+        const int nbk = (BT - r0) / 4;                         // 4 x 4 register blocks per side
+        const int nblk = nbk * (nbk + 1) / 2;
+        for (int blk = tid; blk < nblk; blk += 256) {
+            int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+            while (bi * (bi + 1) / 2 > blk) --bi;
+            while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+            const int bj = blk - bi * (bi + 1) / 2;
+            const int i0 = r0 + 4 * bi, c0 = r0 + 4 * bj;
+            double acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
+#pragma unroll 4
+            for (int kk = j0; kk < j0 + NB; ++kk) {
+                double li[4], lc[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { li[r] = SE(S, i0 + r, kk); lc[r] = SE(S, c0 + r, kk); }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[r][q] = fma(li[r], lc[q], acc[r][q]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (i0 + r >= c0 + q) SE(S, i0 + r, c0 + q) -= acc[r][q];      // lower triangle only: the upper part stays zero
+        }
+        __syncthreads();                                       // the next panel reads what the trailing update wrote
     }
     __syncthreads();
+#ifdef GPCC_PIVOT_PROF
+    long long tp1 = clock64();
+#endif
     if (!a.sweep) {   // forward mode: the diagonal tile keeps the Cholesky factor (upper part zero)
         for (int e = tid; e < BT * BT / 2; e += 256) {
             const int mt = e >> 5, w = e & 31;
@@ -278,45 +347,99 @@ __global__ void __launch_bounds__(256) pivot_kernel(LargeArgs a, int k) {
             *reinterpret_cast<double2*>(tile + 2 * e) = make_double2(SE(S, r, c), SE(S, r, c + 1));
         }
     }
-    // ---- in-place inverse of the lower-triangular factor, last column first (dtrti2, lower) ----
-    // two threads per row share each dot product
+    // ---- in-place inverse of the lower-triangular factor, blocked (LAPACK dtrtri 'L': last block column first) ----------
+    //   A21 <- -Linv22 A21 inv(A11),  A11 <- inv(A11)        with 16-column blocks.
+    // Linv22 A21 (the bulk: R^2/2 x 16 FMAs) runs on warps 0-6 in 2 x 4 register blocks into a staging buffer while warp 7
+    // inverts the 16 x 16 diagonal block (one lane per column, forward substitution in registers); then the staging buffer
+    // is multiplied by the block inverse.  The unblocked form (dtrti2: two threads per row, 2 barriers per column, dot
+    // products of up to 127 terms) took 107 us of the kernel.
     {
-        const int i = tid >> 1, half = tid & 1;
-        for (int j = BT - 1; j >= 0; --j) {
-            double x = 0.0;
-            if (i > j) {
-                double s0 = 0.0, s1 = 0.0;
-                int q = j + 1 + half;
-                for (; q + 2 <= i; q += 4) {
-                    s0 = fma(SE(S, i, q), SE(S, q, j), s0);
-                    s1 = fma(SE(S, i, q + 2), SE(S, q + 2, j), s1);
+        double* Tb = zz + 3 * BT;            // [<=112][16] staging of Linv22 A21 (row-major, stride 17)
+        double* Db = Tb + 112 * 17;          // [16][17] inverse of the diagonal block (row-major)
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int j0 = BT - NB; j0 >= 0; j0 -= NB) {
+            const int r0 = j0 + NB, R = BT - r0;
+            if (warp == 7) {
+                if (lane < NB) {             // column c = lane of inv(A11): x_r = (delta_rc - sum_{q<r} A11(r,q) x_q) / A11(r,r)
+                    const int c = lane;
+                    double x[NB];
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) {
+                        double acc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+                            if (q < r) acc = fma(-SE(S, j0 + r, j0 + q), x[q], acc);
+                        x[r] = (r >= c) ? acc / SE(S, j0 + r, j0 + r) : 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) Db[r * 17 + c] = x[r];
                 }
-                for (; q <= i; q += 2) s0 = fma(SE(S, i, q), SE(S, q, j), s0);
-                x = s0 + s1;
+            } else {
+                // Tb(i, c) = sum_{q = r0..i} Linv22(i, q) A21(q, c), i in [r0, BT), c in [0, 16): 2 rows x 4 columns per thread
+                const int nrb = R / 2;                     // R is a multiple of 16
+                for (int blk = tid; blk < nrb * 4; blk += 224) {
+                    const int ib = blk >> 2, cb = blk & 3;
+                    const int i0 = r0 + 2 * ib, c0 = j0 + 4 * cb;
+                    double acc[2][4];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
+                    for (int q = r0; q <= i0 + 1; ++q) {
+                        const double l0 = (q <= i0) ? SE(S, i0, q) : 0.0, l1 = SE(S, i0 + 1, q);
+                        double av[4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) av[cc] = SE(S, q, c0 + cc);
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) { acc[0][cc] = fma(l0, av[cc], acc[0][cc]); acc[1][cc] = fma(l1, av[cc], acc[1][cc]); }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) Tb[(2 * ib + r) * 17 + 4 * cb + cc] = acc[r][cc];
+                }
             }
-            x += __shfl_xor_sync(0xffffffffu, x, 1);
-            const double ajj = 1.0 / SE(S, j, j);
             __syncthreads();
-            if (half == 0) {
-                if (i > j) SE(S, i, j) = -ajj * x;
-                else if (i == j) SE(S, j, j) = ajj;
+            // A21(i, c) = -sum_{q >= c} Tb(i, q) Dinv(q, c) ;  A11 <- Dinv
+            for (int e = tid; e < R * NB; e += 256) {
+                const int i = e % R, c = e / R;
+                double acc = 0.0;
+                for (int q = c; q < NB; ++q) acc = fma(Tb[i * 17 + q], Db[q * 17 + c], acc);
+                SE(S, r0 + i, j0 + c) = -acc;
+            }
+            {
+                const int r = tid >> 4, c = tid & 15;      // 256 threads = 16 x 16
+                if (r >= c) SE(S, j0 + r, j0 + c) = Db[r * 17 + c];
             }
             __syncthreads();
         }
     }
-    // z = Linv r_k ; quad += z'z ; logdet += 2 sum log L_jj
-    if (tid < BT) {
-        double s0 = 0.0;
-        for (int q = 0; q <= tid; ++q) s0 = fma(SE(S, tid, q), rk[q], s0);
-        zz[tid] = s0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double q = 0.0, ld = 0.0;
-        for (int i = 0; i < BT; ++i) { q = fma(zz[i], zz[i], q); ld += log(ldiag[i]); }
-        a.scal[(size_t)m * 4 + 0] += 2.0 * ld;
-        a.scal[(size_t)m * 4 + 1] += q;
-        if (s_bad && a.info[m] == 0) a.info[m] = k * BT + s_bad;
+#ifdef GPCC_PIVOT_PROF
+    long long tp2 = clock64();
+#endif
+    // z = Linv r_k ; quad += z'z ; logdet += 2 sum log L_jj   (deterministic tree sums)
+    {
+        double zi = 0.0, li = 0.0;
+        if (tid < BT) {
+            for (int q = 0; q <= tid; ++q) zi = fma(SE(S, tid, q), rk[q], zi);
+            zz[tid] = zi;
+            li = log(ldiag[tid]);
+        }
+        double q2 = zi * zi;
+        for (int o = 16; o > 0; o >>= 1) { q2 += __shfl_xor_sync(0xffffffffu, q2, o); li += __shfl_xor_sync(0xffffffffu, li, o); }
+        __shared__ double redq[8], redl[8];
+        if ((tid & 31) == 0) { redq[tid >> 5] = q2; redl[tid >> 5] = li; }
+        __syncthreads();
+        if (tid == 0) {
+            double q = 0.0, ld = 0.0;
+            for (int w = 0; w < 4; ++w) { q += redq[w]; ld += redl[w]; }      // threads 0..127 = warps 0..3
+            a.scal[(size_t)m * 4 + 0] += 2.0 * ld;
+            a.scal[(size_t)m * 4 + 1] += q;
+            if (s_bad && a.info[m] == 0) a.info[m] = k * BT + s_bad;
+#ifdef GPCC_PIVOT_PROF
+            if (m == 0 && k == 1) printf("pivot k=1: load->chol %lld, trtri+store %lld, z/logdet %lld cycles\n", tp1 - tp0, tp2 - tp1, (long long)clock64() - tp2);
+#endif
+        }
     }
     if (tid < BT) a.zk[(size_t)m * BT + tid] = zz[tid];
     // Linv in panel layout: element (c, kk) = Linv[c][kk]  (coalesced: consecutive threads write consecutive doubles)
@@ -739,7 +862,7 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, La
     const int T = w.T;
     const int ntiles = T * (T + 1) / 2;
     const size_t gemm_smem = sizeof(GemmSmem) + 128;
-    const size_t pivot_smem = (size_t)(BT * PLD + 3 * BT) * sizeof(double);
+    const size_t pivot_smem = (size_t)(BT * PLD + 3 * BT + 112 * 17 + 16 * 17) * sizeof(double);
     if (!w.attr_set) {
         cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
         cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
@@ -824,7 +947,11 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
                        LargeTimings* tm) {
     if (!ws.impl) ws.impl = new LargeImpl();
     LargeImpl& w = *static_cast<LargeImpl*>(ws.impl);
-    const int want_B = std::min(b.M, p.N >= 4096 ? 8 : (p.N >= 1024 ? 32 : 128));
+    // Matrices per wave.  The pivot kernel is one CTA per matrix and its 128-column chain is the critical path of a block step;
+    // a wave must hold enough matrices for the DMMA trailing updates of the others to cover it (measured at N = 6144: 8 per
+    // wave 21.6 TFLOP/s, pivot bound; 32 per wave update bound).  ensure() halves the wave if memory is short.
+    static const int wave_env = getenv("GPCC_LARGE_WAVE") ? atoi(getenv("GPCC_LARGE_WAVE")) : 0;
+    const int want_B = std::min(b.M, wave_env > 0 ? wave_env : (p.N >= 8192 ? 16 : (p.N >= 4096 ? 32 : (p.N >= 1024 ? 128 : 512))));
     cudaError_t e = ensure(w, p.N, std::max(want_B, 1));
     if (e != cudaSuccess) return e;
     for (int e0 = 0; e0 < b.M; e0 += w.B) {
