@@ -68,6 +68,7 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad) {
     EvalBatch b;
     b.M = M; b.delays = q.delays.d; b.alpha = q.alpha.d; b.rho = q.rho.d; b.want_grad = want_grad;
     b.ll = q.ll.d; b.grad = q.grad.d; b.info = q.info.d;
+    b.h_delays = q.delays.h; b.h_alpha = q.alpha.h; b.h_rho = q.rho.h;
     const bool prof = p->ctx->profiling;
     q.M = M; q.want_grad = want_grad; q.timed = false;
     if (p->small_path) {
@@ -82,6 +83,7 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad) {
         s.launches += lt.launches;
         s.ms_assembly += lt.ms_assembly; s.ms_factor += lt.ms_factor; s.ms_gradreduce += lt.ms_gradreduce;
         s.ms_eval += lt.ms_assembly + lt.ms_factor + lt.ms_gradreduce;
+        s.shared_prefix_evals += lt.shared_prefix_evals;
     }
     CUDA_TRY(cudaMemcpyAsync(q.ll.h, q.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (want_grad)
@@ -134,7 +136,7 @@ namespace {
 void reset_stats(gpcc_ctx* ctx) {
     for (auto& s : ctx->ds) {
         s.ms_eval = s.ms_assembly = s.ms_factor = s.ms_gradreduce = 0;
-        s.launches = s.evals = s.evals_grad = 0;
+        s.launches = s.evals = s.evals_grad = s.shared_prefix_evals = 0;
         if (s.origin) {   // new time zero (float milliseconds lose resolution far from the origin)
             cudaSetDevice(s.dev);
             cudaStreamSynchronize(s.stream);
@@ -157,10 +159,19 @@ void collect_stats(gpcc_ctx* ctx, const gpcc_problem* p, double ms_total) {
         st.n_eval_launches += s.launches;
         st.n_evals += s.evals;
         st.n_evals_grad += s.evals_grad;
+        st.n_shared_prefix += s.shared_prefix_evals;
     }
     st.path = (p && !p->small_path) ? 1 : 0;
     st.n_devices = (int)ctx->ds.size();
     ctx->stats = st;
+}
+
+// total order on doubles by bit pattern (NaN-safe: the sort keys below may contain invalid hyper-parameters)
+inline bool bits_less(double a, double b, bool& decided) {
+    unsigned long long x, y;
+    std::memcpy(&x, &a, 8); std::memcpy(&y, &b, 8);
+    decided = x != y;
+    return x < y;
 }
 
 struct Timer {
@@ -372,6 +383,17 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
         if (rc) return rc;
         std::vector<int> seq(m);
         for (int c = 0; c < m; ++c) seq[c] = c;
+        if (!p->small_path && o.max_iter <= 0 && !o.theta0_per_candidate && L >= 2) {
+            // fixed-theta sweep on the tiled path (forward-only evaluations): candidates that share the delays of all bands but
+            // the last become neighbours, so that a wave factorises their common leading block once (large_path.cu)
+            std::stable_sort(seq.begin(), seq.end(), [&](int x, int y) {
+                const double* dx = delays + (size_t)idx[x] * L;
+                const double* dy = delays + (size_t)idx[y] * L;
+                bool dec;
+                for (int l = 0; l + 1 < L; ++l) { const bool lt = bits_less(dx[l], dy[l], dec); if (dec) return lt; }
+                return false;
+            });
+        }
         for (size_t c0 = 0; c0 < (size_t)m; c0 += chunk_c) {
             const size_t c1 = std::min<size_t>(m, c0 + chunk_c);
             screen_pack(q0, seq.data() + c0, c1 - c0);
@@ -714,6 +736,17 @@ static int loglik_batch_impl(gpcc_problem* p, int M, const double* delays, const
         EvalSlot& s = ctx->ds[di].slot[0];
         std::vector<int> mine;
         for (int m = di; m < M; m += nd) mine.push_back(m);
+        if (!p->small_path && !want_grad && !theta && L >= 2) {
+            // logL-only sweep on the tiled path: bring evaluations with the same hyper-parameters and the same delays of all
+            // bands but the last next to each other (structure reuse in large_path.cu); results are scattered back by index
+            std::stable_sort(mine.begin(), mine.end(), [&](int x, int y) {
+                bool dec;
+                bool lt = bits_less(rho[x], rho[y], dec); if (dec) return lt;
+                for (int l = 0; l < L; ++l) { lt = bits_less(alpha[(size_t)x * L + l], alpha[(size_t)y * L + l], dec); if (dec) return lt; }
+                for (int l = 0; l + 1 < L; ++l) { lt = bits_less(delays[(size_t)x * L + l], delays[(size_t)y * L + l], dec); if (dec) return lt; }
+                return false;
+            });
+        }
         std::vector<double> jac(n);
         for (size_t c0 = 0; c0 < mine.size(); c0 += chunk) {
             const size_t c1 = std::min(mine.size(), c0 + chunk);

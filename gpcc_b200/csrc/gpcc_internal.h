@@ -33,6 +33,11 @@ struct EvalBatch {
     double* grad = nullptr;          // [M][L+1]
     int* info = nullptr;             // [M]
     int mode_postb = 0;              // 1 (tiled path only): factor Sobs + K WITHOUT B (the fitted state of postb / pred, :241-250)
+    // host mirrors of delays / alpha / rho (optional): the tiled path compares consecutive evaluations on the host to find runs
+    // that share the hyper-parameters and the delays of all bands but the last (structure reuse, large_path.cu)
+    const double* h_delays = nullptr;
+    const double* h_alpha = nullptr;
+    const double* h_rho = nullptr;
     double* dump_chol = nullptr;     // optional [M][N*N] dense column-major Cholesky factor (lower, upper part zero); tiled path,
                                      // forward mode only (the fitted state behind postb / pred, fitstate.cu)
 };
@@ -77,6 +82,7 @@ struct LargeWorkspace {
 struct LargeTimings {
     double ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
     long long launches = 0;
+    long long shared_prefix_evals = 0;   // evaluations whose leading block was factorised by another matrix of their wave
 };
 cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& ws, cudaStream_t stream, bool profile,
                        LargeTimings* timings);

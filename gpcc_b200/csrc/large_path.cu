@@ -51,6 +51,8 @@ __device__ __forceinline__ int pl_off(int r, int c) { return (((c >> 2) * 16 + (
 struct LargeArgs {
     int N, L, T, Np, kid;
     int sweep;          // 1: full symmetric sweep (inverse, gradient); 0: forward only (Cholesky, logL)
+    int Tp;             // > 0 (forward mode only): the first Tp block rows / columns are IDENTICAL in all matrices of the wave
+                        // (same hyper-parameters, same delays of all bands but the last): matrix 0 computes them for everybody
     int mode_postb;
     double* mats;       // [B][ntiles][TILE_ELEMS]
     double* Pws;        // [B][T][TILE_ELEMS]   gathered column, panel layout
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(DevProblem p, EvalBatch b
     while ((size_t)I * (I + 1) / 2 > (size_t)tix) --I;
     while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tix) ++I;
     const int J = tix - I * (I + 1) / 2;
+    if (a.Tp && m > 0 && I < a.Tp) return;        // shared prefix tile: assembled (and factorised) once, by matrix 0
     const int tid = threadIdx.x;
     if (tid < BT) {
         const int i = I * BT + tid;
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(256) pivot_kernel(LargeArgs a, int k) {
     double* ldiag = rk + BT;           // [BT] diagonal of L
     __shared__ int s_bad;
     const int m = blockIdx.x, tid = threadIdx.x;
+    if (a.Tp && k < a.Tp && m > 0) return;         // shared prefix: matrix 0 factorises the diagonal block for the whole wave
     const int ty = tid >> 4, tx = tid & 15;
     double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(k, k) * TILE_ELEMS;
     for (int e = tid; e < BT * BT / 2; e += 256) {           // coalesced double2 reads of the tile layout
@@ -435,6 +439,10 @@ __global__ void __launch_bounds__(256) pivot_kernel(LargeArgs a, int k) {
             for (int w = 0; w < 4; ++w) { q += redq[w]; ld += redl[w]; }      // threads 0..127 = warps 0..3
             a.scal[(size_t)m * 4 + 0] += 2.0 * ld;
             a.scal[(size_t)m * 4 + 1] += q;
+            if (a.Tp && k == a.Tp - 1) {             // log-det and quadratic form of the shared prefix, for the other matrices
+                a.scal[2] = a.scal[0];
+                a.scal[3] = a.scal[1];
+            }
             if (s_bad && a.info[m] == 0) a.info[m] = k * BT + s_bad;
 #ifdef GPCC_PIVOT_PROF
             if (m == 0 && k == 1) printf("pivot k=1: load->chol %lld, trtri+store %lld, z/logdet %lld cycles\n", tp1 - tp0, tp2 - tp1, (long long)clock64() - tp2);
@@ -488,6 +496,7 @@ __global__ void __launch_bounds__(256) gather_kernel(LargeArgs a, int k, int I0)
     const int m = blockIdx.y;
     int I = I0 + blockIdx.x;
     if (a.sweep && I >= k) ++I;           // skip the pivot block row
+    if (a.Tp && m > 0 && k < a.Tp && I < a.Tp) return;   // shared prefix rows
     const double* mat = a.mats + (size_t)m * a.mat_stride;
     double* out = a.Pws + ((size_t)m * a.T + I) * TILE_ELEMS;
     if (I > k) {
@@ -518,8 +527,10 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I
     const int m = blockIdx.y, which = blockIdx.z;
     int I = I0 + blockIdx.x;
     if (a.sweep && I >= k) ++I;
+    if (a.Tp && m > 0 && k < a.Tp && I < a.Tp) return;   // shared prefix rows
+    const int mL = (a.Tp && k < a.Tp) ? 0 : m;           // the pivot block of a shared step lives in matrix 0
     const double* gA = a.Pws + ((size_t)m * a.T + I) * TILE_ELEMS;
-    const double* gB = (which == 0 ? a.Linv : a.Dinv) + (size_t)m * TILE_ELEMS;
+    const double* gB = (which == 0 ? a.Linv : a.Dinv) + (size_t)mL * TILE_ELEMS;
     double acc[4][8][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -542,7 +553,7 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I
         // r_I -= X_I z_k  : partial dot over this warp's 64 columns, combined through shared memory
         double* red = reinterpret_cast<double*>(smraw);      // reuse stage memory (main loop is finished)
         __syncthreads();
-        const double* z = a.zk + (size_t)m * BT;
+        const double* z = a.zk + (size_t)mL * BT;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             double s = 0.0;
@@ -615,9 +626,11 @@ __global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k, int 
         else { I = Ir + k + skip; J = Jr + k + skip; }
     }
     (void)T;
+    if (a.Tp && m > 0 && I < a.Tp) return;         // tile of the shared prefix (J <= I < Tp): updated once, in matrix 0
+    const int mB = (a.Tp && k < a.Tp && J < a.Tp) ? 0 : m;   // panel rows inside the shared prefix exist in matrix 0 only
     const double* xw = a.Xws + (size_t)(k & 1) * a.x_parity_stride;
     const double* gA = xw + ((size_t)m * a.T + I) * TILE_ELEMS;
-    const double* gB = xw + ((size_t)m * a.T + J) * TILE_ELEMS;
+    const double* gB = xw + ((size_t)mB * a.T + J) * TILE_ELEMS;
     double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ro0 = (warp & 3) * 4, co0 = (warp >> 2) * 8;
@@ -731,8 +744,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(DevProblem p, EvalBatch b
     __shared__ double red[8];
     __shared__ double srow_band[MAX_BANDS];
     const int m = blockIdx.x, e = e0 + m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int info = a.info[m];
-    const double ll = -0.5 * ((double)a.N * LOG2PI + a.scal[(size_t)m * 4 + 0] + a.scal[(size_t)m * 4 + 1]);
+    int info = a.info[m];
+    double logdet = a.scal[(size_t)m * 4 + 0], quad = a.scal[(size_t)m * 4 + 1];
+    if (a.Tp && m > 0) {                          // add the shared prefix (computed in matrix 0)
+        logdet += a.scal[2];
+        quad += a.scal[3];
+        const int i0 = a.info[0];
+        if (i0 != 0 && i0 <= a.Tp * BT) info = i0; // the first failing leading minor lies inside the prefix
+    }
+    const double ll = -0.5 * ((double)a.N * LOG2PI + logdet + quad);
     if (tid == 0) {
         b.ll[e] = info ? -INFINITY : ll;
         if (b.info) b.info[e] = info;
@@ -850,11 +870,12 @@ cudaError_t ensure(LargeImpl& w, int N, int want_B) {
 }
 
 template <int KID>
-cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, LargeImpl& w, cudaStream_t st, bool profile,
+cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, int Tp, LargeImpl& w, cudaStream_t st, bool profile,
                      LargeTimings* tm) {
     LargeArgs a;
     a.N = p.N; a.L = p.L; a.T = w.T; a.Np = w.Np; a.kid = KID;
     a.sweep = b.want_grad ? 1 : 0;
+    a.Tp = a.sweep ? 0 : Tp;
     a.mode_postb = b.mode_postb;
     a.mats = w.mats; a.Pws = w.Pws; a.Xws = w.Xws; a.Linv = w.Linv; a.Dinv = w.Dinv; a.rvec = w.rvec; a.zk = w.zk;
     a.scal = w.scal; a.info = w.info; a.tsh = w.tsh; a.av = w.av; a.part = w.part; a.epart = w.epart; a.mat_stride = w.mat_stride;
@@ -954,16 +975,47 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
     const int want_B = std::min(b.M, wave_env > 0 ? wave_env : (p.N >= 8192 ? 16 : (p.N >= 4096 ? 32 : (p.N >= 1024 ? 128 : 512))));
     cudaError_t e = ensure(w, p.N, std::max(want_B, 1));
     if (e != cudaSuccess) return e;
-    for (int e0 = 0; e0 < b.M; e0 += w.B) {
-        const int nb = std::min(w.B, b.M - e0);
+    // Structure reuse across the grid (src/delayedCovariance.jl:23-31: block (l, m) of the covariance depends
+    // on tau_l - tau_m only).  Evaluations that share the hyper-parameters and the delays of all bands but the last have an
+    // identical leading principal block; in forward (Cholesky) mode a wave made of such a run factorises that block ONCE.
+    // The callers sort fixed-theta sweeps so that these runs are long (api.cu); here consecutive runs are detected on the host
+    // mirrors of the parameters and cut into balanced waves.
+    static const bool no_share = getenv("GPCC_LARGE_NO_SHARE") != nullptr;
+    const int L = p.L;
+    const int Tp_full = (L >= 2 && !b.want_grad && !no_share && b.h_delays && b.h_alpha && b.h_rho) ? p.band_start[L - 1] / BT : 0;
+    auto same_prefix = [&](int x, int y) {
+        if (b.h_rho[x] != b.h_rho[y]) return false;
+        for (int l = 0; l < L; ++l) if (b.h_alpha[(size_t)x * L + l] != b.h_alpha[(size_t)y * L + l]) return false;
+        for (int l = 0; l + 1 < L; ++l) if (b.h_delays[(size_t)x * L + l] != b.h_delays[(size_t)y * L + l]) return false;
+        return true;
+    };
+    long long shared_evals = 0;
+    std::vector<int> rl;                                     // rl[x] = length of the run with a common prefix that starts at x
+    if (Tp_full > 0) {
+        rl.assign(b.M, 1);
+        for (int x = b.M - 2; x >= 0; --x) if (same_prefix(x, x + 1)) rl[x] = rl[x + 1] + 1;
+    }
+    constexpr int MIN_RUN = 4;
+    for (int e0 = 0; e0 < b.M;) {
+        int nb = 0, Tp = 0;
+        if (Tp_full > 0 && rl[e0] >= MIN_RUN) {              // balanced waves inside the run
+            const int nwaves = (rl[e0] + w.B - 1) / w.B;
+            nb = (rl[e0] + nwaves - 1) / nwaves;
+            Tp = Tp_full;
+            shared_evals += nb - 1;
+        } else {                                             // no sharing: up to a full wave, but stop where a long run begins
+            while (nb < w.B && e0 + nb < b.M && !(nb > 0 && Tp_full > 0 && rl[e0 + nb] >= MIN_RUN)) ++nb;
+        }
         switch (p.kernel_id) {
-            case K_OU:  e = run_wave<K_OU>(p, b, e0, nb, w, stream, profile, tm); break;
-            case K_RBF: e = run_wave<K_RBF>(p, b, e0, nb, w, stream, profile, tm); break;
-            case K_M32: e = run_wave<K_M32>(p, b, e0, nb, w, stream, profile, tm); break;
-            default:    e = run_wave<K_M52>(p, b, e0, nb, w, stream, profile, tm); break;
+            case K_OU:  e = run_wave<K_OU>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
+            case K_RBF: e = run_wave<K_RBF>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
+            case K_M32: e = run_wave<K_M32>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
+            default:    e = run_wave<K_M52>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
         }
         if (e != cudaSuccess) return e;
+        e0 += nb;
     }
+    tm->shared_prefix_evals += shared_evals;
     return cudaSuccess;
 }
 

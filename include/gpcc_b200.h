@@ -71,6 +71,8 @@ typedef struct gpcc_stats {
     long long n_evals_grad;     /* ... of which with gradient                                       */
     int    path;                /* 0 = fused register-resident small-N kernel, 1 = tiled large-N    */
     int    n_devices;
+    long long n_shared_prefix;  /* tiled path, logL only: evaluations whose leading block (all bands but the
+                                   last) was factorised by another evaluation of their wave (structure reuse) */
 } gpcc_stats;
 
 int         gpcc_version(void);

@@ -315,6 +315,61 @@ def test_large_path_matches_oracle(ctx, nper, kernel):
     assert np.array_equal(again[0], ll) and np.array_equal(again[1], grad)      # deterministic
 
 
+def test_structure_reuse_across_the_grid(ctx):
+    """Fixed-theta sweep on the tiled path: candidates that share the hyper-parameters and the delays of all
+    bands but the last share the leading block of the covariance (src/delayedCovariance.jl:23-31); a wave factorises it once.
+    Same numbers as without sharing (to rounding: only the summation order of log-det / quadratic form differs), for any
+    order of the candidates, ragged bands, and through the iterations=0 grid driver."""
+    import os, subprocess, sys
+    t, y, s, d = gpcc_b200.synthetic_bands([150, 130, 93], seed=12)                 # band boundaries not on tile boundaries
+    p = Problem(t, y, s, "matern32", ctx)
+    c2, c3 = np.arange(0.0, 3.01, 0.5), np.arange(0.0, 6.01, 0.25)
+    delays = np.array([[0.0, a, b] for b in c3 for a in c2])                          # d1 fastest: the shared prefix is scattered
+    M = len(delays)
+    alpha, rho = np.tile([1.1, 1.9, 2.4], (M, 1)), np.full(M, 2.7)
+    ll, info = p.loglik_batch(delays, alpha, rho)
+    st = ctx.stats()
+    assert st["path"] == 1 and np.all(info == 0)
+    assert st["n_shared_prefix"] >= M - 2 * len(c2)                                    # all but one evaluation per wave reuse the block
+    op = oracle.Problem(t, y, s, "matern32")
+    for m in (0, 17, M - 1):
+        assert abs(ll[m] - op.loglik(delays[m], alpha[m], rho[m])) / abs(ll[m]) < LL_RTOL
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\nimport gpcc_b200\n"
+            "t, y, s, d = gpcc_b200.synthetic_bands([150, 130, 93], seed=12)\n"
+            "p = gpcc_b200.Problem(t, y, s, 'matern32')\n"
+            "z = np.load(sys.argv[1]); ll, info = p.loglik_batch(z['delays'], z['alpha'], z['rho'])\n"
+            "assert gpcc_b200.default_context().stats()['n_shared_prefix'] == 0\n"
+            "np.save(sys.argv[2], ll)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(os.path.join(tmp, "in.npz"), delays=delays, alpha=alpha, rho=rho)
+        r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, "in.npz"), os.path.join(tmp, "out.npy")],
+                           env=dict(os.environ, GPCC_LARGE_NO_SHARE="1"), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        ll_plain = np.load(os.path.join(tmp, "out.npy"))
+    assert np.max(np.abs(ll - ll_plain) / np.abs(ll_plain)) < 1e-13
+    perm = np.random.default_rng(3).permutation(M)
+    ll_p, _ = p.loglik_batch(delays[perm], alpha[perm], rho[perm])
+    assert np.array_equal(ll_p, ll[perm])                                              # the internal ordering does not leak out
+    # mixed hyper-parameters: only equal (alpha, rho, prefix) may share
+    alpha2 = alpha.copy(); alpha2[::3, 0] = 1.3
+    ll2, _ = p.loglik_batch(delays, alpha2, rho)
+    for m in (0, 1, 2, 3):
+        assert abs(ll2[m] - op.loglik(delays[m], alpha2[m], rho[m])) / abs(ll2[m]) < LL_RTOL
+    # the grid driver with iterations = 0 (the north-star fixed-theta posterior) goes through the same reuse
+    th = np.concatenate([np.log(np.expm1(np.array([1.1, 1.9, 2.4]))), [np.log((2.7 - 0.1) / (300.0 - 2.7))]])[None]
+    r = p.grid_posterior(delays, th, iterations=0, rhomin=0.1, rhomax=300.0)
+    assert ctx.stats()["n_shared_prefix"] > 0 and abs(r["posterior"].sum() - 1.0) < 1e-12
+    a_, r_ = r["alpha"][0], r["rho"][0]
+    ll3, _ = p.loglik_batch(delays, np.tile(a_, (M, 1)), np.full(M, r_))
+    assert np.allclose(r["loglikel"], ll3, rtol=1e-13)
+    # a matrix that is not positive definite inside the shared block is reported for every candidate of the wave
+    t2 = [a.copy() for a in t]; t2[0][5] = t2[0][4]
+    pb = Problem(t2, y, [np.zeros_like(a) for a in s], "rbf", ctx)
+    llb, infob = pb.loglik_batch(delays[:14], alpha[:14], np.full(14, 0.05))
+    assert np.all(llb == -np.inf) and np.all(infob > 0) and np.all(infob <= 150)
+
+
 def test_large_path_not_positive_definite_reports_leading_minor(ctx):
     t, y, s, d = gpcc_b200.synthetic_bands([200, 200], seed=2)
     t[1][150] = t[1][10]                                   # duplicated time stamp in band 2 (global index 350)
