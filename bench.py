@@ -168,6 +168,41 @@ def run_reference(args, rank, out):
     out.flush()
 
 
+def run_single_process(args, out):
+    """One process, N devices: gpcc_ctx_create(ndev=N) -> one host thread per device, ncclCommInitAll + ncclAllGather inside the
+    library (what the Julia shim's default context does with GPCC_B200_NDEV=N).  Same workload and step as the default mode."""
+    import torch
+    import gpcc_b200
+    t, y, s, delays, label = make_workload(args.workload, args.gpus if args.scaling == "weak" else 1)
+    theta0 = gpcc_b200.initial_solutions(y, 1, 1, INITIALRANDOM, RHOMIN, RHOMAX)[0][0]
+    ctx = gpcc_b200.Context(ndev=args.gpus, profiling=True)
+    problem = gpcc_b200.Problem(t, y, s, gpcc_b200.matern32, ctx)
+    flush = [torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda:%d" % d) for d in range(args.gpus)]
+    def sync():
+        for d in range(args.gpus):
+            torch.cuda.synchronize(d)
+    for _ in range(max(args.warmup, 3)):
+        problem.grid_posterior(delays, theta0, iterations=ITERATIONS, rhomin=RHOMIN, rhomax=RHOMAX)
+    times = []
+    for i in range(args.steps):
+        for f in flush:
+            f.fill_(float(i))
+        sync()
+        t0 = time.perf_counter()
+        res = problem.grid_posterior(delays, theta0, iterations=ITERATIONS, rhomin=RHOMIN, rhomax=RHOMAX)   # synchronous call
+        times.append(time.perf_counter() - t0)
+    st = ctx.stats()
+    ms = float(np.mean(times)) * 1e3
+    line = {"metric": METRIC, "value": len(delays) / (ms * 1e-3), "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": common_config(label),
+            "details": {"mode": "single process, gpcc_ctx_create(ndev=%d): one host thread per device, ncclCommInitAll + ncclAllGather in the library" % args.gpus,
+                        "timing": "host wall clock around the synchronous call (devices idle before and after), L2 flushed between steps",
+                        "kernel_ms_per_step_max_over_devices": st["ms_eval_kernels"], "posterior_sum": float(np.sum(res["posterior"]))}}
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner) write to fd 1, so fd 1 is
     # pointed at stderr for the duration of the run and the JSON line is written to the saved descriptor.
@@ -181,6 +216,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--cpu-per-core", type=int, default=4, help="candidates per host core in the CPU sample")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process driving --gpus N devices through gpcc_ctx_create(ndev=N) (the layout a single Julia process uses) instead of one rank per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
@@ -190,6 +227,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, real_stdout)
         return
+    if args.single_process:
+        return run_single_process(args, real_stdout)
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
     if args.gpus > 1 and world == 1:
