@@ -935,7 +935,9 @@ int posterior_on_devices(gpcc_ctx* ctx, int L, int M, const GatherIO& io, const 
         for (auto& s : ctx->ds) devs.push_back(s.dev);
         std::string err;
         ctx->nccl = nccl_bridge_create(devs, err);
-        if (!ctx->nccl) return fail(2000, "NCCL unavailable for the multi-device allgather: " + err);
+        // one process holds every device's results on the host already: without NCCL the posterior is still computed on
+        // device 0 (a multi-process communicator cannot do without it and fails in gpcc_ctx_comm_init_rank instead)
+        if (!ctx->nccl) return gpcc_getprobabilities(ctx, M, io.ll, logprior, out_post);
     }
     std::vector<double*> d_send(nd), d_recv(nd);
     std::vector<cudaStream_t> streams(nd);
