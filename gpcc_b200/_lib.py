@@ -13,7 +13,7 @@ EXPORTS = [
     "gpcc_grid_posterior", "gpcc_getprobabilities", "gpcc_postb", "gpcc_predict", "gpcc_predict_loglik",
     "gpcc_fit_options_default", "gpcc_fit_state_create", "gpcc_fit_state_destroy", "gpcc_fit_state_postb",
     "gpcc_fit_state_predict", "gpcc_fit_state_predict_loglik", "gpcc_fit_state_factorisations",
-    "gpcc_comm_unique_id", "gpcc_ctx_comm_init_rank",
+    "gpcc_comm_unique_id", "gpcc_ctx_comm_init_rank", "gpcc_fit_state_sample",
 ]
 
 
@@ -73,6 +73,7 @@ def load():
     lib.gpcc_fit_state_predict.argtypes = [vp, ip, dp, dp, dp, dp]
     lib.gpcc_fit_state_predict_loglik.argtypes = [vp, ip, dp, dp, dp, dp, ip]
     lib.gpcc_fit_state_factorisations.argtypes = [vp]
+    lib.gpcc_fit_state_sample.argtypes = [vp, C.c_ulonglong, C.c_int, dp, dp]
     lib.gpcc_comm_unique_id.argtypes = [C.c_char_p]
     lib.gpcc_ctx_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     for name in EXPORTS:

@@ -336,6 +336,14 @@ class FitState:
         check(_lib.load().gpcc_fit_state_predict_loglik(self._h, _i(nt), _d(tt), _d(yt), _d(st), C.byref(ll), C.byref(info)))
         return ll.value, info.value
 
+    def sample(self, seed, nsamples=1, return_z=False):
+        """Draws f ~ N(0, K + Sobs) at the state's hyper-parameters on the device: [nsamples][N] (simulatedata.jl:128-145)."""
+        N = self.problem.N
+        f = np.empty((int(nsamples), N))
+        z = np.empty((int(nsamples), N)) if return_z else None
+        check(_lib.load().gpcc_fit_state_sample(self._h, int(seed), int(nsamples), _d(f), _d(z)))
+        return (f, z) if return_z else f
+
     @property
     def factorisations(self):
         return int(_lib.load().gpcc_fit_state_factorisations(self._h))
@@ -464,6 +472,28 @@ def gpccgrid(tarray, yarray, stdarray, candidatedelays, *, kernel, iterations, s
         theta0 = initial_solutions(yarray, seed, 1, initialrandom, rhomin, rhomax)[0][0]
     return p.grid_posterior(candidatedelays, theta0, iterations=iterations, rhomin=rhomin, rhomax=rhomax,
                             logprior=logprior)
+
+
+def simulatedata_device(tarray, *, delays, alpha, b, rho=3.5, sigma=0.75, kernel=OU, seed=1, ctx=None):
+    """The reference's simulator (src/simulatedata.jl:96-162) with the O(N^3) part on the device: the latent process is drawn
+    from N(0, C + 1e-6 I), C = delayedCovariance(kernel, alpha, delays, rho, tarray) (:128; the 1e-6 stands in for the
+    eigenvalue clamp of :132-138), through the tiled Cholesky and the device generator of gpcc_fit_state_sample; scaling,
+    offsets and observation noise (:151-159, alpha applied a second time as the reference does) are host arithmetic.
+    Returns (tarray, yarray, stdarray).  Meant for large synthetic benchmarks (N in the thousands)."""
+    tarray = [_f64(a) for a in tarray]
+    L = len(tarray)
+    dummy = [np.arange(len(a), dtype=np.float64) for a in tarray]              # the prior of b needs a variance; unused by the draw
+    p = Problem(tarray, dummy, [np.full(len(a), 1e-3) for a in tarray], kernel, ctx)
+    st = p.fit_state(delays, alpha, rho)
+    f = st.sample(seed, 1)[0]
+    st.close(); p.close()
+    rg = np.random.default_rng(seed)
+    y, mark = [], 0
+    for l in range(L):
+        n = len(tarray[l])
+        y.append(f[mark:mark + n] * float(alpha[l]) + float(b[l]) + sigma * rg.standard_normal(n))
+        mark += n
+    return tarray, y, [sigma * np.ones(len(a)) for a in tarray]
 
 
 def repaired_logpdf(mu, Sigma, y, minimumeigenvalue=1e-6):

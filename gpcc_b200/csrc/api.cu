@@ -669,6 +669,7 @@ int gpcc_problem_create(gpcc_ctx* ctx, int L, const int* n_per_band, const doubl
         }
     p->small_path = small_path_supports(N);
     p->pd.resize(ctx->ds.size());
+    struct Guard { gpcc_problem* p; ~Guard() { if (p) gpcc_problem_destroy(p); } } guard{p};   // a failed upload frees what exists
     for (size_t di = 0; di < ctx->ds.size(); ++di) {
         auto& d = p->pd[di];
         d.dev = ctx->ds[di].dev;
@@ -689,6 +690,7 @@ int gpcc_problem_create(gpcc_ctx* ctx, int L, const int* n_per_band, const doubl
         d.dp.t = d.t; d.dp.resid = d.resid; d.dp.y = d.y; d.dp.s2 = d.s2; d.dp.sigb = d.sigb; d.dp.band = d.band;
         for (int l = 0; l <= L; ++l) d.dp.band_start[l] = p->band_start[l];
     }
+    guard.p = nullptr;
     *out = p;
     return 0;
 }

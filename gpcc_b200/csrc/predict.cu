@@ -381,6 +381,56 @@ __global__ void __launch_bounds__(1024) chol_logpdf_kernel(int n, double* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Sampling from the fitted process (the draw of src/simulatedata.jl:128-145, Y ~ MvNormal(0, C), on the device).
+// Counter-based generator: Philox-4x32-10 (Salmon et al. 2011), counter = (index, 0, sample stream, 0), key = seed; two
+// 53-bit uniforms per call -> Box-Muller pair.  Reproducible for a given seed whatever the launch geometry.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__global__ void normal_kernel(size_t n, unsigned long long seed, double* __restrict__ z) {
+    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    for (size_t pair = (size_t)blockIdx.x * blockDim.x + threadIdx.x; 2 * pair < n; pair += (size_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((unsigned)pair, (unsigned)(pair >> 32), 0x47504343u, 0u), key);
+        const double u1 = ((double)(((unsigned long long)(r.x >> 5) << 26) | (r.y >> 6)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)(((unsigned long long)(r.z >> 5) << 26) | (r.w >> 6)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z[2 * pair] = rad * cs;
+        if (2 * pair + 1 < n) z[2 * pair + 1] = rad * sn;
+    }
+}
+
+// f[s][i] = sum_{j <= i} Lc(i, j) z[s][j]: one thread per row, the rows of the column-major factor coalesced across threads
+__global__ void __launch_bounds__(256) trmv_lower_kernel(int N, int ns, const double* __restrict__ Lc, const double* __restrict__ z,
+                                                         double* __restrict__ f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int s0 = blockIdx.y * 4; s0 < ns; s0 += gridDim.y * 4) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j <= i; ++j) {
+            const double l = Lc[(size_t)j * N + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (s0 + q < ns) acc[q] = fma(l, z[(size_t)(s0 + q) * N + j], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (s0 + q < ns) f[(size_t)(s0 + q) * N + i] = acc[q];
+    }
+}
+
 int check_hyper(const gpcc_problem* p, const double* delays, const double* alpha, double rho) {
     if (!p || !delays || !alpha) return fail(-1, "NULL argument");
     for (int l = 0; l < p->L; ++l) {
@@ -584,6 +634,26 @@ int gpcc_fit_state_predict_loglik(gpcc_fit_state* s, const int* ntest_per_band, 
 }
 
 long long gpcc_fit_state_factorisations(const gpcc_fit_state* s) { return s ? s->n_factorisations : -1; }
+
+int gpcc_fit_state_sample(gpcc_fit_state* s, unsigned long long seed, int nsamples, double* out_f, double* out_z) {
+    if (!s || !out_f) return fail(-1, "NULL argument");
+    if (nsamples < 1) return fail(-2, "nsamples < 1");
+    const int N = s->N;
+    const size_t n = (size_t)N * nsamples;
+    DeviceState& ds = s->p->ctx->ds[0];
+    CUDA_TRY(cudaSetDevice(s->dev));
+    cudaStream_t st = ds.stream;
+    CUDA_TRY(s->Z.reserve(n));          // deviates
+    CUDA_TRY(s->G.reserve(n));          // draws
+    normal_kernel<<<(int)std::min<size_t>(1184, (n / 2 + 255) / 256 + 1), 256, 0, st>>>(n, seed, s->Z.d);
+    trmv_lower_kernel<<<dim3((N + 255) / 256, std::min((nsamples + 3) / 4, 1024)), 256, 0, st>>>(N, nsamples, s->Lc, s->Z.d, s->G.d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_f, s->G.d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_z) CUDA_TRY(cudaMemcpyAsync(out_z, s->Z.d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ds.launches += 2;
+    return 0;
+}
 
 int gpcc_postb(gpcc_problem* p, const double* delays, const double* alpha, double rho, double* out_mu, double* out_Sigma) {
     gpcc_fit_state* s = nullptr;

@@ -153,6 +153,12 @@ int gpcc_fit_state_predict(gpcc_fit_state* s, const int* ntest_per_band, const d
                            double* out_sd, double* out_Sigma);
 int gpcc_fit_state_predict_loglik(gpcc_fit_state* s, const int* ntest_per_band, const double* ttest,
                                   const double* ytest, const double* sigmatest, double* out_ll, int* out_info);
+/* Draws from the process at the state's hyper-parameters, on the device: out_f[s][N] = Lc z_s with Lc Lc' = K + Sobs and
+ * z_s ~ N(0, I) from a counter-based generator (Philox-4x32-10 + Box-Muller, reproducible per seed).  This is the sampling
+ * step of the reference's simulator (src/simulatedata.jl:128-145: Y ~ MvNormal(0, C), C = delayedCovariance(OU, ...)) for
+ * large synthetic benchmarks; the light curves around it (scaling, offsets, noise: :151-159) are O(N) host
+ * arithmetic in both shims.  out_z (may be NULL) receives the deviates [nsamples][N].                                  */
+int gpcc_fit_state_sample(gpcc_fit_state* s, unsigned long long seed, int nsamples, double* out_f, double* out_z);
 /* diagnostics: number of N^3 factorisations this state has run (1 for its whole life).               */
 long long gpcc_fit_state_factorisations(const gpcc_fit_state* s);
 

@@ -370,6 +370,61 @@ def test_structure_reuse_across_the_grid(ctx):
     assert np.all(llb == -np.inf) and np.all(infob > 0) and np.all(infob <= 150)
 
 
+def test_device_sampler_and_simulator(ctx):
+    """gpcc_fit_state_sample: f = Lc z with Lc the cached factor of K + Sobs and z from the device's Philox / Box-Muller
+    generator (the draw of src/simulatedata.jl:128-145).  Exactness through the returned deviates, distribution through
+    moments, reproducibility through the seed; then the simulator built around it, fitted back."""
+    t, y, s, d = gpcc_b200.synthetic_bands([90, 80, 70], seed=8)
+    p = Problem(t, y, s, "OU", ctx)
+    alpha, rho = np.array([1.0, 1.5, 2.0]), 3.5
+    st = p.fit_state(d, alpha, rho)
+    f, z = st.sample(seed=123, nsamples=3, return_z=True)
+    op = oracle.Problem(t, y, s, "OU")
+    K = oracle.delayed_covariance("OU", alpha, d, rho, t) + np.diag(op.sobs)
+    Lc = np.linalg.cholesky(K)
+    assert np.max(np.abs(f - z @ Lc.T)) < 1e-10 * np.max(np.abs(f))
+    f2 = st.sample(seed=123, nsamples=3)
+    assert np.array_equal(f, f2) and not np.array_equal(f, st.sample(seed=124, nsamples=3))
+    zz = st.sample(seed=5, nsamples=500, return_z=True)[1].ravel()                 # 120 000 deviates
+    assert abs(zz.mean()) < 0.01 and abs(zz.var() - 1.0) < 0.01 and abs(np.mean(zz ** 3)) < 0.03 and abs(np.mean(zz ** 4) - 3.0) < 0.06
+    assert len(np.unique(zz)) == len(zz)
+    big = st.sample(seed=9, nsamples=2000)
+    emp = big.T @ big / 2000.0
+    assert np.max(np.abs(emp - K)) < 0.25 * np.max(np.abs(K))                        # sample covariance -> K
+    st.close()
+    # simulator -> fit: the posterior over a small delay grid peaks at the simulated delay
+    rg = np.random.default_rng(1)
+    tt = [np.sort(rg.uniform(0, 60, 140)), np.sort(rg.uniform(0, 60, 120))]
+    tt, yy, ss = gpcc_b200.simulatedata_device(tt, delays=[0.0, 3.0], alpha=[1.0, 1.5], b=[6.0, 15.0], rho=3.5, sigma=0.3, seed=4, ctx=ctx)
+    assert [len(a) for a in yy] == [140, 120] and abs(np.mean(yy[1]) - 15.0) < 3.0
+    cands = np.arange(0.0, 6.01, 0.5)
+    res = gpcc_b200.gpccgrid(tt, yy, ss, np.stack([np.zeros_like(cands), cands], 1), kernel=gpcc_b200.OU, iterations=300, rhomax=50.0, ctx=ctx)
+    assert abs(cands[np.argmax(res["posterior"])] - 3.0) <= 0.5
+
+
+def test_path_crossover_sizes_match_oracle(ctx):
+    """N = 199 is the largest problem of the fused register-resident path, N = 200 the smallest of the tiled path: both
+    sides of the dispatch against the oracle (logL forward-only and with gradient), and a fit on each side."""
+    for nper, path in (([70, 69, 60], 0), ([70, 70, 60], 1)):
+        t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=17)
+        op, p = oracle.Problem(t, y, s, "matern52"), Problem(t, y, s, "matern52", ctx)
+        rg = np.random.default_rng(6)
+        delays = np.zeros((4, 3)); delays[:, 1:] = rg.uniform(0, 5, (4, 2))
+        alpha, rho = rg.uniform(0.6, 2.5, (4, 3)), rg.uniform(1.0, 6.0, 4)
+        ll, grad, info = p.loglik_batch(delays, alpha, rho, want_grad=True)
+        assert ctx.stats()["path"] == path and np.all(info == 0)
+        ll_f, _ = p.loglik_batch(delays, alpha, rho)
+        for m in range(4):
+            rl, rgd = op.loglik_grad(delays[m], alpha[m], rho[m])
+            assert abs(ll[m] - rl) / abs(rl) < LL_RTOL and abs(ll_f[m] - rl) / abs(rl) < LL_RTOL
+            assert np.max(np.abs(grad[m] - rgd)) / np.max(np.abs(rgd)) < GRAD_RTOL
+        th = gpcc_b200.initial_solutions(y, 3, 1, 4, 0.1, 100.0)[0][0]
+        r = p.fit_batch(delays[:2], th, iterations=300, rhomin=0.1, rhomax=100.0)
+        for m in range(2):
+            o = oracle.gpcc(t, y, s, kernel="matern52", delays=delays[m], iterations=300, rhomin=0.1, rhomax=100.0, theta0=th[None], optimizer="lbfgs")
+            assert abs(r["loglikel"][m] - o[0]) < FIT_ATOL or r["loglikel"][m] > o[0]
+
+
 def test_large_path_not_positive_definite_reports_leading_minor(ctx):
     t, y, s, d = gpcc_b200.synthetic_bands([200, 200], seed=2)
     t[1][150] = t[1][10]                                   # duplicated time stamp in band 2 (global index 350)
