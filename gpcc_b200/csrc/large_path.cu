@@ -158,6 +158,58 @@ __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* __rest
     }
 }
 
+// Half-tile form of the main loop for the trailing update: 4 warps compute the 128 x 64 column half `h` of a tile (warp w: rows
+// 32 w.., all 64 columns).  164 registers x 128 threads and 72 KB of staging let THREE such CTAs share an SM, so the global
+// load / store of one CTA's accumulators (the C tile: 131 KB per tile and step, not overlapped inside a CTA) hides under the
+// DMMAs of the others, and every scheduler holds three warps instead of two.
+struct GemmSmemHalf {
+    double a[STAGES][CHUNK_ELEMS];
+    double b[STAGES][CHUNK_ELEMS / 2];
+    uint64_t full[STAGES];
+};
+
+__device__ __forceinline__ void stage_half(GemmSmemHalf& sm, int s, const double* gA, const double* gB, int ch, int h) {
+    mbar_expect_tx(&sm.full[s], (CHUNK_ELEMS + CHUNK_ELEMS / 2) * sizeof(double));
+    bulk_g2s(sm.a[s], gA + (size_t)ch * CHUNK_ELEMS, CHUNK_ELEMS * sizeof(double), &sm.full[s]);
+#pragma unroll
+    for (int k4 = 0; k4 < KCH / 4; ++k4)      // the column half is 8 of the 16 row groups of every 4-deep slice: 2 KB each
+        bulk_g2s(sm.b[s] + k4 * 256, gB + (size_t)ch * CHUNK_ELEMS + (size_t)(k4 * 16 + 8 * h) * 32, 256 * sizeof(double), &sm.full[s]);
+}
+
+__device__ __forceinline__ void gemm_mainloop_half(GemmSmemHalf& sm, const double* __restrict__ gA, const double* __restrict__ gB, int h,
+                                                   double (&acc)[4][8][2]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ro0 = warp * 4;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s) stage_half(sm, s, gA, gB, s, h);
+#pragma unroll 1
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int s = ch % STAGES;
+        mbar_wait(&sm.full[s], (ch / STAGES) & 1);
+        const double* sa = sm.a[s];
+        const double* sb = sm.b[s];
+#pragma unroll
+        for (int k4 = 0; k4 < KCH / 4; ++k4) {
+            double av[4], bv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = -sa[((k4 * 16 + ro0 + i) << 5) + lane];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = sb[((k4 * 8 + j) << 5) + lane];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+        }
+        __syncthreads();   // everyone is done with stage s
+        if (tid == 0 && ch + STAGES < NCHUNK) stage_half(sm, s, gA, gB, ch + STAGES, h);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // prep: shifted times, per-point alpha, right-hand side
 // ---------------------------------------------------------------------------------------------------------------
@@ -604,13 +656,8 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I
 // ---------------------------------------------------------------------------------------------------------------
 // phase 0: every tile; phase 1: only the tiles of block row/column k+1 (what the next pivot and panel need: the
 // look-ahead part, issued on the critical stream); phase 2: all the others (issued on the bulk stream).
-__global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k, int phase) {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
-    const int m = blockIdx.y;
-    const int tix = blockIdx.x;
-    const int T = a.T, n1 = k + 1;
-    int I, J;
+__device__ __forceinline__ void update_tile_of(const LargeArgs& a, int k, int phase, int tix, int& I, int& J) {
+    const int n1 = k + 1;
     if (phase == 1) {
         if (a.sweep) {              // (n1, J) for J in [0, n1] \ {k}  (n1 tiles), then (I, n1) for I > n1
             if (tix < n1) { I = n1; J = tix + (tix >= k); }
@@ -625,6 +672,47 @@ __global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k, int 
         if (a.sweep) { I = Ir + (Ir >= k ? skip : 0); J = Jr + (Jr >= k ? skip : 0); }
         else { I = Ir + k + skip; J = Jr + k + skip; }
     }
+}
+
+// half-tile form (default): blockIdx.x = 2 * tile + column half
+__global__ void __launch_bounds__(128, 3) update_half_kernel(LargeArgs a, int k, int phase) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GemmSmemHalf& sm = *reinterpret_cast<GemmSmemHalf*>(smraw);
+    const int m = blockIdx.y, h = blockIdx.x & 1;
+    int I, J;
+    update_tile_of(a, k, phase, blockIdx.x >> 1, I, J);
+    if (a.Tp && m > 0 && I < a.Tp) return;         // tile of the shared prefix (J <= I < Tp): updated once, in matrix 0
+    const int mB = (a.Tp && k < a.Tp && J < a.Tp) ? 0 : m;   // panel rows inside the shared prefix exist in matrix 0 only
+    const double* xw = a.Xws + (size_t)(k & 1) * a.x_parity_stride;
+    const double* gA = xw + ((size_t)m * a.T + I) * TILE_ELEMS;
+    const double* gB = xw + ((size_t)mB * a.T + J) * TILE_ELEMS;
+    double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ro0 = warp * 4, co0 = h * 8;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(tile + (((ro0 + i) * 16 + co0 + j) << 6) + 2 * lane);
+            acc[i][j][0] = v.x;
+            acc[i][j][1] = v.y;
+        }
+    gemm_mainloop_half(sm, gA, gB, h, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<double2*>(tile + (((ro0 + i) * 16 + co0 + j) << 6) + 2 * lane) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+__global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k, int phase) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    const int m = blockIdx.y;
+    const int T = a.T;
+    int I, J;
+    update_tile_of(a, k, phase, blockIdx.x, I, J);
     (void)T;
     if (a.Tp && m > 0 && I < a.Tp) return;         // tile of the shared prefix (J <= I < Tp): updated once, in matrix 0
     const int mB = (a.Tp && k < a.Tp && J < a.Tp) ? 0 : m;   // panel rows inside the shared prefix exist in matrix 0 only
@@ -887,9 +975,16 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, in
     if (!w.attr_set) {
         cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
         cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+        cudaFuncSetAttribute(update_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GemmSmemHalf) + 128));
         cudaFuncSetAttribute(pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pivot_smem);
         w.attr_set = true;
     }
+    static const bool full_tiles = getenv("GPCC_LARGE_FULL_TILES") != nullptr;   // A/B switch: one 8-warp CTA per tile
+    const size_t half_smem = sizeof(GemmSmemHalf) + 128;
+    auto launch_update = [&](int ntile, int phase, int kk, cudaStream_t strm) {
+        if (full_tiles) update_kernel<<<dim3(ntile, nb), 256, gemm_smem, strm>>>(a, kk, phase);
+        else update_half_kernel<<<dim3(2 * ntile, nb), 128, half_smem, strm>>>(a, kk, phase);
+    };
     long long launches = 0;
     if (profile) cudaEventRecord(w.ev[0], st);
     prep_kernel<<<dim3((w.Np + 255) / 256, nb), 256, 0, st>>>(p, b, e0, a);
@@ -916,18 +1011,18 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, in
         const int n_rest = n_rest_side > 0 ? n_rest_side * (n_rest_side + 1) / 2 : 0;
         if (!lookahead || !has_next) {
             if (bulk_pending[(k + 1) & 1]) { cudaStreamWaitEvent(st, w.ev_bulk[(k + 1) & 1], 0); bulk_pending[(k + 1) & 1] = false; }
-            update_kernel<<<dim3(nI * (nI + 1) / 2, nb), 256, gemm_smem, st>>>(a, k, 0);
+            launch_update(nI * (nI + 1) / 2, 0, k, st);
             ++launches;
             continue;
         }
         cudaEventRecord(w.ev_panel[k & 1], st);
         // the critical tiles were last written by the bulk part of update k-1
         if (bulk_pending[(k + 1) & 1]) { cudaStreamWaitEvent(st, w.ev_bulk[(k + 1) & 1], 0); bulk_pending[(k + 1) & 1] = false; }
-        update_kernel<<<dim3(n_crit, nb), 256, gemm_smem, st>>>(a, k, 1);
+        launch_update(n_crit, 1, k, st);
         ++launches;
         if (n_rest > 0) {
             cudaStreamWaitEvent(w.bulk, w.ev_panel[k & 1], 0);
-            update_kernel<<<dim3(n_rest, nb), 256, gemm_smem, w.bulk>>>(a, k, 2);
+            launch_update(n_rest, 2, k, w.bulk);
             cudaEventRecord(w.ev_bulk[k & 1], w.bulk);
             bulk_pending[k & 1] = true;
             ++launches;
