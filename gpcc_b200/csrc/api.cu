@@ -286,6 +286,9 @@ int fit_shard_device(gpcc_problem* p, int di, const std::vector<int>& idx, const
         fprintf(stderr, "[gpcc fit] %d candidates on %llu CTAs: kernel span %.2f ms, mean CTA exit at %.2f ms (%.1f %% of the CTA-time busy), "
                         "%llu gradient + %llu forward evaluations\n", m, s.fit_counters.h[6], span, mean_exit, 100.0 * mean_exit / span,
                 s.fit_counters.h[1], s.fit_counters.h[2]);
+        if (s.fit_counters.h[7])
+            fprintf(stderr, "[gpcc fit] thread-0 optimiser time: %.1f cycles per evaluation (build with -DGPCC_FIT_PROF)\n",
+                    (double)s.fit_counters.h[7] / (double)(s.fit_counters.h[1] + s.fit_counters.h[2]));
     }
     s.launches += 1;
     s.evals += (long long)(s.fit_counters.h[1] + s.fit_counters.h[2]);

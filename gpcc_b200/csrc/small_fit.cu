@@ -172,7 +172,15 @@ small_fit_kernel(DevProblem p, FitParams fp, FitBuffers fb, int T, int ctl_offse
         if (cand >= fp.M) break;
         if (tid < L) c.delays[tid] = fb.delays[(size_t)cand * L + tid];
         for (;;) {
-            if (tid == 0) advance<OPT>(c, L, fp, fb, lo);
+            if (tid == 0) {
+#ifdef GPCC_FIT_PROF
+                const long long ta = clock64();
+#endif
+                advance<OPT>(c, L, fp, fb, lo);
+#ifdef GPCC_FIT_PROF
+                atomicAdd(fb.counters + 7, (unsigned long long)(clock64() - ta));
+#endif
+            }
             __syncthreads();
             if (c.phase == PH_DONE) break;
             if (tid <= L) unpack_parallel(c, tid, L, fp);
