@@ -402,6 +402,46 @@ def test_device_sampler_and_simulator(ctx):
     assert abs(cands[np.argmax(res["posterior"])] - 3.0) <= 0.5
 
 
+def test_random_problems_match_oracle(ctx):
+    """Seeded sweep over random shapes: 1-5 bands of 2-90 points (total N from a handful to ~330, both paths, every residue of
+    N modulo the 8-wide register tiles and the 128-wide HBM tiles that the sizes happen to hit), all four kernels, logL
+    forward-only and with gradient against the oracle; plus one fitted candidate per problem against the oracle's L-BFGS."""
+    rg = np.random.default_rng(2026)
+    kernels = list(oracle.KERNELS)
+    seen_paths = set()
+    for trial in range(28):
+        L = int(rg.integers(1, 6))
+        nper = [int(v) for v in rg.integers(2, 91, L)]
+        if trial % 7 == 0:
+            nper = [int(v) for v in rg.integers(60, 120, 3)]                  # make sure the tiled path is visited
+        L = len(nper)
+        kernel = kernels[trial % 4]
+        t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=100 + trial, span=float(rg.uniform(8.0, 40.0)))
+        op, p = oracle.Problem(t, y, s, kernel), Problem(t, y, s, kernel, ctx)
+        M = 3
+        delays = np.zeros((M, L)); delays[:, 1:] = rg.uniform(-4, 9, (M, L - 1))
+        alpha, rho = rg.uniform(0.3, 3.0, (M, L)), np.exp(rg.uniform(np.log(0.3), np.log(60.0), M))
+        ll, grad, info = p.loglik_batch(delays, alpha, rho, want_grad=True)
+        seen_paths.add(ctx.stats()["path"])
+        ll_f, info_f = p.loglik_batch(delays, alpha, rho)
+        assert np.all(info == 0) and np.all(info_f == 0), (trial, nper, kernel)
+        for m in range(M):
+            rl, rgd = op.loglik_grad(delays[m], alpha[m], rho[m])
+            assert abs(ll[m] - rl) <= LL_RTOL * abs(rl) and abs(ll_f[m] - rl) <= LL_RTOL * abs(rl), (trial, nper, kernel, m)
+            assert np.max(np.abs(grad[m] - rgd)) <= GRAD_RTOL * max(np.max(np.abs(rgd)), 1e-3), (trial, nper, kernel, m)
+        if trial % 4 == 0:
+            th = gpcc_b200.initial_solutions(y, trial + 1, 1, 3, 0.1, 80.0)[0][0]
+            r = p.fit_batch(delays[:1], th, iterations=400, rhomin=0.1, rhomax=80.0)
+            o = oracle.gpcc(t, y, s, kernel=kernel, delays=delays[0], iterations=400, rhomin=0.1, rhomax=80.0, theta0=th[None], optimizer="lbfgs")
+            # a scale that collapsed onto its 1e-8 floor (band decoupled from the latent process, SURVEY.md section 7) leaves logL
+            # rising by ~1e-6 in total as theta_l -> -infinity: both optimisers sit in that degenerate valley and stop at
+            # different depths; such candidates carry no posterior mass.  Everywhere else the 1e-6 contract is enforced.
+            tol = 1e-5 if np.min(r["alpha"][0]) < 1e-6 else FIT_ATOL
+            assert r["loglikel"][0] >= o[0] - tol, (trial, nper, kernel, r["loglikel"][0], o[0])
+        p.close()
+    assert seen_paths == {0, 1}
+
+
 def test_path_crossover_sizes_match_oracle(ctx):
     """N = 199 is the largest problem of the fused register-resident path, N = 200 the smallest of the tiled path: both
     sides of the dispatch against the oracle (logL forward-only and with gradient), and a fit on each side."""
