@@ -376,7 +376,7 @@ def main():
         # configs[3] (3 bands x 2048 points, N=6144, matern52): the tiled large-N path on the north-star workload, a fixed-theta
         # posterior over the 100 x 100 delay grid (0:0.2:19.8)^2, one blocked Cholesky (N^3/3 flop, DMMA trailing updates) per
         # candidate (iterations=0: screening only).  Every rank takes 1 250 candidates (its share of the 8-GPU run), so at 8 GPUs
-        # this IS the full 10^4-candidate grid of the "< 10 s" target and below it is the first 1 250 x N candidates.
+        # this IS the full 10^4-candidate grid of the "< 10 s" target and below it is the share of the first N ranks of that run.
         try:
             from gpcc_b200 import synthetic
             t4, y4, s4, _ = synthetic.synthetic_bands([2048, 2048, 2048], seed=4)
@@ -384,7 +384,11 @@ def main():
             c4 = np.arange(0.0, 19.8001, 0.2)
             grid4 = np.array([[0.0, a, b] for b in c4 for a in c4])
             share = int(os.environ.get("GPCC_BENCH_CFG4_SHARE", "1250"))
-            d4 = grid4[: share * world]
+            # below 8 GPUs: the candidates that ranks 0 .. world-1 own in the 8-GPU run (candidate m -> rank m mod 8), in grid order, so
+            # that rank j of this run works on exactly the share of rank j of the full run (runs of 50 candidates with a common
+            # tau_2), not on a corner of the grid with 12-candidate stubs
+            sel4 = np.array([m for m in range(len(grid4)) if m % 8 < min(world, 8)])
+            d4 = grid4[sel4][: share * world]
             th4 = np.concatenate([np.log(np.expm1(np.array([1.0, 2.2, 4.0]))), [np.log((3.5 - RHOMIN) / (RHOMAX - 3.5))]])[None]
             p4.grid_posterior(d4[: 16 * world], th4, iterations=0, rhomin=RHOMIN, rhomax=RHOMAX)            # warm-up (workspace allocation)
             barrier()
