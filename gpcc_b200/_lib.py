@@ -28,7 +28,7 @@ class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_eval_kernels", C.c_double), ("ms_assembly", C.c_double),
                 ("ms_factor", C.c_double), ("ms_gradreduce", C.c_double), ("n_eval_launches", C.c_longlong),
                 ("n_evals", C.c_longlong), ("n_evals_grad", C.c_longlong), ("path", C.c_int),
-                ("n_devices", C.c_int), ("n_shared_prefix", C.c_longlong)]
+                ("n_devices", C.c_int), ("n_shared_prefix", C.c_longlong), ("n_tau_cache", C.c_longlong), ("assembly_bytes", C.c_longlong)]
 
 
 class GpccError(RuntimeError):

@@ -84,6 +84,8 @@ int gpcc::launch_eval(gpcc_problem* p, int di, int slot, int M, int want_grad) {
         s.ms_assembly += lt.ms_assembly; s.ms_factor += lt.ms_factor; s.ms_gradreduce += lt.ms_gradreduce;
         s.ms_eval += lt.ms_assembly + lt.ms_factor + lt.ms_gradreduce;
         s.shared_prefix_evals += lt.shared_prefix_evals;
+        s.tau_cache_evals += lt.tau_cache_evals;
+        s.assembly_bytes += lt.assembly_bytes;
     }
     CUDA_TRY(cudaMemcpyAsync(q.ll.h, q.ll.d, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (want_grad)
@@ -136,7 +138,7 @@ namespace {
 void reset_stats(gpcc_ctx* ctx) {
     for (auto& s : ctx->ds) {
         s.ms_eval = s.ms_assembly = s.ms_factor = s.ms_gradreduce = 0;
-        s.launches = s.evals = s.evals_grad = s.shared_prefix_evals = 0;
+        s.launches = s.evals = s.evals_grad = s.shared_prefix_evals = s.tau_cache_evals = s.assembly_bytes = 0;
         if (s.origin) {   // new time zero (float milliseconds lose resolution far from the origin)
             cudaSetDevice(s.dev);
             cudaStreamSynchronize(s.stream);
@@ -160,6 +162,8 @@ void collect_stats(gpcc_ctx* ctx, const gpcc_problem* p, double ms_total) {
         st.n_evals += s.evals;
         st.n_evals_grad += s.evals_grad;
         st.n_shared_prefix += s.shared_prefix_evals;
+        st.n_tau_cache += s.tau_cache_evals;
+        st.assembly_bytes = std::max(st.assembly_bytes, s.assembly_bytes);   // like ms_assembly: the busiest device
     }
     st.path = (p && !p->small_path) ? 1 : 0;
     st.n_devices = (int)ctx->ds.size();

@@ -83,6 +83,8 @@ struct LargeTimings {
     double ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
     long long launches = 0;
     long long shared_prefix_evals = 0;   // evaluations whose leading block was factorised by another matrix of their wave
+    long long assembly_bytes = 0;        // HBM bytes moved by the covariance assembly kernels (tiles written; cache imports read + written)
+    long long tau_cache_evals = 0;       // evaluations that imported the band-1 steps of their last band from the last-band cache
 };
 cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& ws, cudaStream_t stream, bool profile,
                        LargeTimings* timings);

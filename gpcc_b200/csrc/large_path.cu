@@ -30,6 +30,8 @@
 #include <cstdlib>
 #include <vector>
 #include <cstdio>
+#include <cstring>
+#include <map>
 
 namespace gpcc {
 namespace {
@@ -69,7 +71,26 @@ struct LargeArgs {
     double* epart;      // [B][ntiles]
     size_t mat_stride;  // doubles per matrix
     size_t x_parity_stride;   // Xws is double buffered by step parity (look-ahead: update k still reads X_k while panel k+1 writes)
+    // Last-band cache (forward mode, three bands, band boundaries on tile boundaries; see large_eval).  Pivots k < Tq lie in band 1,
+    // block rows I >= Tc in the last band.  What steps k < Tq do to the last band's rows -- the panels X_I^(k), the state of block
+    // (3,3) and of r_3 after step Tq-1 -- depends on the LAST delay only: cmode 1 (FILL) computes it once per distinct value and
+    // exports it to slot[m]; cmode 2 (USE) imports it instead of recomputing it for every candidate.
+    int Tq, Tc, cmode;
+    const int* eidx;    // [B] evaluation index of matrix m (nullptr: e0 + m)
+    const int* slot;    // [B] cache slot of matrix m
+    double *XC, *AC, *RC;
+    size_t xc_stride, ac_stride, rc_stride;   // doubles per slot
 };
+__device__ __forceinline__ double* xc_tile(const LargeArgs& a, int m, int k, int I) {
+    return a.XC + (size_t)a.slot[m] * a.xc_stride + ((size_t)k * (a.T - a.Tc) + (I - a.Tc)) * TILE_ELEMS;
+}
+__device__ __forceinline__ double* ac_tile(const LargeArgs& a, int m, int I, int J) {
+    return a.AC + (size_t)a.slot[m] * a.ac_stride + tile_index(I - a.Tc, J - a.Tc) * TILE_ELEMS;
+}
+// FILL never touches the middle band; USE leaves the last band's rows alone while the pivot is in band 1
+__device__ __forceinline__ bool cache_skips_row(const LargeArgs& a, int k, int I) {
+    return (a.cmode == 1 && I >= a.Tq && I < a.Tc) || (a.cmode == 2 && k < a.Tq && I >= a.Tc);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk async copy (TMA engine, 1-D), DMMA
@@ -214,7 +235,7 @@ __device__ __forceinline__ void gemm_mainloop_half(GemmSmemHalf& sm, const doubl
 // prep: shifted times, per-point alpha, right-hand side
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void prep_kernel(DevProblem p, EvalBatch b, int e0, LargeArgs a) {
-    const int m = blockIdx.y, e = e0 + m;
+    const int m = blockIdx.y, e = a.eidx ? a.eidx[m] : e0 + m;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.Np; i += gridDim.x * blockDim.x) {
         double ts = 0.0, al = 0.0, r = 0.0;
         if (i < a.N) {
@@ -223,6 +244,7 @@ __global__ void prep_kernel(DevProblem p, EvalBatch b, int e0, LargeArgs a) {
             al = b.alpha[(size_t)e * a.L + bi];
             r = a.mode_postb ? p.y[i] : p.resid[i];
         }
+        if (a.cmode == 2 && i >= a.Tc * BT) r = a.RC[(size_t)a.slot[m] * a.rc_stride + (i - a.Tc * BT)];   // r_3 after step Tq-1
         a.tsh[(size_t)m * a.Np + i] = ts;
         a.av[(size_t)m * a.Np + i] = al;
         a.rvec[(size_t)m * a.Np + i] = r;
@@ -240,7 +262,7 @@ template <int KID>
 __global__ void __launch_bounds__(256) assemble_kernel(DevProblem p, EvalBatch b, int e0, LargeArgs a) {
     __shared__ double tr[BT], tc[BT], ar[BT], ac[BT], dr[BT], sr[BT];
     __shared__ int br[BT], bc[BT];
-    const int m = blockIdx.y, e = e0 + m;
+    const int m = blockIdx.y, e = a.eidx ? a.eidx[m] : e0 + m;
     // decode lower tile index
     const int tix = blockIdx.x;
     int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
@@ -249,6 +271,16 @@ __global__ void __launch_bounds__(256) assemble_kernel(DevProblem p, EvalBatch b
     const int J = tix - I * (I + 1) / 2;
     if (a.Tp && m > 0 && I < a.Tp) return;        // shared prefix tile: assembled (and factorised) once, by matrix 0
     const int tid = threadIdx.x;
+    if (a.cmode == 1 && ((I >= a.Tq && I < a.Tc) || (J >= a.Tq && J < a.Tc))) return;   // FILL: nothing of the middle band
+    if (a.cmode == 2 && I >= a.Tc) {
+        if (J < a.Tq) return;                     // block (3,1) is only ever read by the cached steps
+        if (J >= a.Tc) {                          // block (3,3) as steps 0 .. Tq-1 leave it
+            const double2* src = reinterpret_cast<const double2*>(ac_tile(a, m, I, J));
+            double2* dst = reinterpret_cast<double2*>(a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS);
+            for (int q = tid; q < TILE_ELEMS / 2; q += 256) dst[q] = src[q];
+            return;
+        }
+    }
     if (tid < BT) {
         const int i = I * BT + tid;
         tr[tid] = a.tsh[(size_t)m * a.Np + i];
@@ -549,6 +581,7 @@ __global__ void __launch_bounds__(256) gather_kernel(LargeArgs a, int k, int I0)
     int I = I0 + blockIdx.x;
     if (a.sweep && I >= k) ++I;           // skip the pivot block row
     if (a.Tp && m > 0 && k < a.Tp && I < a.Tp) return;   // shared prefix rows
+    if (cache_skips_row(a, k, I)) return;
     const double* mat = a.mats + (size_t)m * a.mat_stride;
     double* out = a.Pws + ((size_t)m * a.T + I) * TILE_ELEMS;
     if (I > k) {
@@ -580,6 +613,7 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(LargeArgs a, int k, int I
     int I = I0 + blockIdx.x;
     if (a.sweep && I >= k) ++I;
     if (a.Tp && m > 0 && k < a.Tp && I < a.Tp) return;   // shared prefix rows
+    if (cache_skips_row(a, k, I)) return;
     const int mL = (a.Tp && k < a.Tp) ? 0 : m;           // the pivot block of a shared step lives in matrix 0
     const double* gA = a.Pws + ((size_t)m * a.T + I) * TILE_ELEMS;
     const double* gB = (which == 0 ? a.Linv : a.Dinv) + (size_t)mL * TILE_ELEMS;
@@ -682,9 +716,12 @@ __global__ void __launch_bounds__(128, 3) update_half_kernel(LargeArgs a, int k,
     int I, J;
     update_tile_of(a, k, phase, blockIdx.x >> 1, I, J);
     if (a.Tp && m > 0 && I < a.Tp) return;         // tile of the shared prefix (J <= I < Tp): updated once, in matrix 0
+    if (cache_skips_row(a, k, J) || (a.cmode == 1 && I >= a.Tq && I < a.Tc)) return;
+    const bool cached = a.cmode == 2 && k < a.Tq && I >= a.Tc;   // last band, pivot in band 1: only block (3,2) is updated,
+    if (cached && J < a.Tq) return;                              // with the cached panel of the last band
     const int mB = (a.Tp && k < a.Tp && J < a.Tp) ? 0 : m;   // panel rows inside the shared prefix exist in matrix 0 only
     const double* xw = a.Xws + (size_t)(k & 1) * a.x_parity_stride;
-    const double* gA = xw + ((size_t)m * a.T + I) * TILE_ELEMS;
+    const double* gA = cached ? xc_tile(a, m, k, I) : xw + ((size_t)m * a.T + I) * TILE_ELEMS;
     const double* gB = xw + ((size_t)mB * a.T + J) * TILE_ELEMS;
     double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -715,9 +752,12 @@ __global__ void __launch_bounds__(256, 1) update_kernel(LargeArgs a, int k, int 
     update_tile_of(a, k, phase, blockIdx.x, I, J);
     (void)T;
     if (a.Tp && m > 0 && I < a.Tp) return;         // tile of the shared prefix (J <= I < Tp): updated once, in matrix 0
+    if (cache_skips_row(a, k, J) || (a.cmode == 1 && I >= a.Tq && I < a.Tc)) return;
+    const bool cached = a.cmode == 2 && k < a.Tq && I >= a.Tc;   // last band, pivot in band 1: only block (3,2) is updated,
+    if (cached && J < a.Tq) return;                              // with the cached panel of the last band
     const int mB = (a.Tp && k < a.Tp && J < a.Tp) ? 0 : m;   // panel rows inside the shared prefix exist in matrix 0 only
     const double* xw = a.Xws + (size_t)(k & 1) * a.x_parity_stride;
-    const double* gA = xw + ((size_t)m * a.T + I) * TILE_ELEMS;
+    const double* gA = cached ? xc_tile(a, m, k, I) : xw + ((size_t)m * a.T + I) * TILE_ELEMS;
     const double* gB = xw + ((size_t)mB * a.T + J) * TILE_ELEMS;
     double* tile = a.mats + (size_t)m * a.mat_stride + tile_index(I, J) * TILE_ELEMS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -881,6 +921,32 @@ __global__ void __launch_bounds__(256) finalize_kernel(DevProblem p, EvalBatch b
     }
 }
 
+// last-band cache, FILL side: the panels of step k (rows of the last band) ...
+__global__ void __launch_bounds__(256) export_x_kernel(LargeArgs a, int k) {
+    const int m = blockIdx.y, I = a.Tc + blockIdx.x;
+    const double2* src = reinterpret_cast<const double2*>(a.Xws + (size_t)(k & 1) * a.x_parity_stride + ((size_t)m * a.T + I) * TILE_ELEMS);
+    double2* dst = reinterpret_cast<double2*>(xc_tile(a, m, k, I));
+    for (int q = threadIdx.x; q < TILE_ELEMS / 2; q += 256) dst[q] = src[q];
+}
+// ... and, after step Tq-1, the state of block (3,3) (blockIdx.x < number of its tiles) and of r_3 (the last block)
+__global__ void __launch_bounds__(256) export_state_kernel(LargeArgs a) {
+    const int m = blockIdx.y, nC = a.T - a.Tc, ntc = nC * (nC + 1) / 2;
+    if ((int)blockIdx.x == ntc) {
+        double* dst = a.RC + (size_t)a.slot[m] * a.rc_stride;
+        const double* src = a.rvec + (size_t)m * a.Np + (size_t)a.Tc * BT;
+        for (int q = threadIdx.x; q < nC * BT; q += 256) dst[q] = src[q];
+        return;
+    }
+    const int tix = blockIdx.x;
+    int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) / 2 > tix) --I;
+    while ((I + 1) * (I + 2) / 2 <= tix) ++I;
+    const int J = tix - I * (I + 1) / 2;
+    const double2* src = reinterpret_cast<const double2*>(a.mats + (size_t)m * a.mat_stride + tile_index(I + a.Tc, J + a.Tc) * TILE_ELEMS);
+    double2* dst = reinterpret_cast<double2*>(ac_tile(a, m, I + a.Tc, J + a.Tc));
+    for (int q = threadIdx.x; q < TILE_ELEMS / 2; q += 256) dst[q] = src[q];
+}
+
 // dense column-major Cholesky factor (lower triangle, zeros above) out of the tile layout: forward mode only
 __global__ void dump_chol_kernel(EvalBatch b, int e0, LargeArgs a) {
     const int m = blockIdx.y, e = e0 + m;
@@ -899,13 +965,25 @@ struct LargeImpl {
     double *mats = nullptr, *Pws = nullptr, *Xws = nullptr, *Linv = nullptr, *Dinv = nullptr, *rvec = nullptr, *zk = nullptr,
            *scal = nullptr, *tsh = nullptr, *av = nullptr, *part = nullptr, *epart = nullptr;
     int* info = nullptr;
+    int *eidx_d = nullptr, *slot_d = nullptr;    // [B] per-wave maps of the last-band cache
+    double *XC = nullptr, *AC = nullptr, *RC = nullptr;   // the cache itself: [slots][...]
+    int cache_slots = 0, cache_T = 0, cache_Tc = 0, cache_Tq = 0;
+    size_t xc_stride = 0, ac_stride = 0, rc_stride = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t bulk = nullptr;                 // second stream: the bulk of each trailing update (look-ahead)
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_bulk[2] = {nullptr, nullptr}, ev_join = nullptr;
     bool attr_set = false;
+    void release_cache() {
+        for (double* q : {XC, AC, RC}) if (q) cudaFree(q);
+        XC = AC = RC = nullptr;
+        cache_slots = 0;
+    }
     void release() {
         for (double* p : {mats, Pws, Xws, Linv, Dinv, rvec, zk, scal, tsh, av, part, epart}) if (p) cudaFree(p);
         if (info) cudaFree(info);
+        for (int* q : {eidx_d, slot_d}) if (q) cudaFree(q);
+        eidx_d = slot_d = nullptr;
+        release_cache();
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto& e : ev_panel) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto& e : ev_bulk) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -946,6 +1024,8 @@ cudaError_t ensure(LargeImpl& w, int N, int want_B) {
     ALLOC(w.part, (size_t)B * T * T * BT)
     ALLOC(w.epart, (size_t)B * ntiles)
     ALLOC(w.info, (size_t)B)
+    ALLOC(w.eidx_d, (size_t)B)
+    ALLOC(w.slot_d, (size_t)B)
 #undef ALLOC
     for (auto& ev : w.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
     for (auto& ev : w.ev_panel) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -957,9 +1037,37 @@ cudaError_t ensure(LargeImpl& w, int N, int want_B) {
     return cudaSuccess;
 }
 
+// Last-band cache: room for `slots` distinct values of the last delay.  Returns false (no error) when it does not fit.
+bool ensure_cache(LargeImpl& w, int slots, int Tq, int Tc) {
+    const int nC = w.T - Tc;
+    if (w.cache_slots >= slots && w.cache_T == w.T && w.cache_Tc == Tc && w.cache_Tq == Tq) return true;
+    w.release_cache();
+    const int wanted = slots;
+    w.xc_stride = (size_t)Tq * nC * TILE_ELEMS;
+    w.ac_stride = (size_t)nC * (nC + 1) / 2 * TILE_ELEMS;
+    w.rc_stride = (size_t)nC * BT;
+    const size_t bytes = (size_t)slots * (w.xc_stride + w.ac_stride + w.rc_stride) * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 2) return false;
+    // head-room (a grid has ~10^2 distinct delays per band): a first call with a few candidates must not force a re-allocation,
+    // and its allocator stall, into the next one
+    while (slots < 128 && (size_t)(2 * slots) * (bytes / wanted) <= free_b / 8) slots *= 2;
+    if (cudaMalloc(&w.XC, (size_t)slots * w.xc_stride * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&w.AC, (size_t)slots * w.ac_stride * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&w.RC, (size_t)slots * w.rc_stride * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        w.release_cache();
+        return false;
+    }
+    w.cache_slots = slots; w.cache_T = w.T; w.cache_Tc = Tc; w.cache_Tq = Tq;
+    return true;
+}
+
+// cmode 0: plain wave.  1: FILL wave of the last-band cache (matrix m = evaluation h_eidx[m], result into slot h_slot[m]; only the
+// steps k < Tq run, nothing is reported).  2: USE wave (matrix m reads slot h_slot[m]).
 template <int KID>
 cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, int Tp, LargeImpl& w, cudaStream_t st, bool profile,
-                     LargeTimings* tm) {
+                     LargeTimings* tm, int cmode = 0, int Tq = 0, int Tc = 0, const int* h_eidx = nullptr, const int* h_slot = nullptr) {
     LargeArgs a;
     a.N = p.N; a.L = p.L; a.T = w.T; a.Np = w.Np; a.kid = KID;
     a.sweep = b.want_grad ? 1 : 0;
@@ -968,7 +1076,19 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, in
     a.mats = w.mats; a.Pws = w.Pws; a.Xws = w.Xws; a.Linv = w.Linv; a.Dinv = w.Dinv; a.rvec = w.rvec; a.zk = w.zk;
     a.scal = w.scal; a.info = w.info; a.tsh = w.tsh; a.av = w.av; a.part = w.part; a.epart = w.epart; a.mat_stride = w.mat_stride;
     a.x_parity_stride = (size_t)w.B * w.T * TILE_ELEMS;
+    a.cmode = a.sweep ? 0 : cmode; a.Tq = Tq; a.Tc = Tc;
+    a.eidx = nullptr; a.slot = w.slot_d;
+    a.XC = w.XC; a.AC = w.AC; a.RC = w.RC; a.xc_stride = w.xc_stride; a.ac_stride = w.ac_stride; a.rc_stride = w.rc_stride;
+    if (a.cmode) {      // pageable source: the copy is staged before the call returns; ordered behind the previous wave on `st`
+        cudaMemcpyAsync(w.slot_d, h_slot, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (a.cmode == 1) {
+            cudaMemcpyAsync(w.eidx_d, h_eidx, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, st);
+            a.eidx = w.eidx_d;
+            a.Tp = Tq;      // the matrices of a FILL wave share band 1 (same hyper-parameters, same first delay)
+        }
+    }
     const int T = w.T;
+    const int ksteps = a.cmode == 1 ? Tq : T;
     const int ntiles = T * (T + 1) / 2;
     const size_t gemm_smem = sizeof(GemmSmem) + 128;
     const size_t pivot_smem = (size_t)(BT * PLD + 3 * BT + 112 * 17 + 16 * 17) * sizeof(double);
@@ -990,13 +1110,23 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, in
     prep_kernel<<<dim3((w.Np + 255) / 256, nb), 256, 0, st>>>(p, b, e0, a);
     assemble_kernel<KID><<<dim3(ntiles, nb), 256, 0, st>>>(p, b, e0, a);
     launches += 2;
+    {   // HBM bytes the assembly of this wave moves (what the kernel's early exits leave): tiles written, imported tiles read + written
+        auto tri = [](long long n) { return n * (n + 1) / 2; };
+        const long long nC = T - Tc, nM = Tc - Tq;
+        long long own = ntiles, lead = 0;                    // tiles per matrix, extra tiles of matrix 0 (the shared prefix)
+        if (a.Tp) { lead = tri(a.Tp); own = ntiles - lead; }
+        if (a.cmode == 1) own = nC * Tq + tri(nC);           // FILL: blocks (3,1) and (3,3)
+        if (a.cmode == 2) own = (ntiles - tri(Tc)) - nC * Tq + tri(nC) + (a.Tp ? 0 : tri(Tc));   // USE: (3,2) written, (3,3) read + written
+        tm->assembly_bytes += ((long long)nb * own + lead) * (long long)(TILE_ELEMS * sizeof(double));
+        (void)nM;
+    }
     if (profile) cudaEventRecord(w.ev[1], st);
     // Look-ahead schedule on two streams.  Critical stream `st`: pivot_k, gather_k, panel_k, then the part of update k
     // that touches block row/column k+1, so that pivot/gather/panel of step k+1 start while the bulk stream is still
     // busy with the rest of update k (the pivot kernel occupies one SM per matrix; without look-ahead the other SMs idle).
     static const bool lookahead = !(getenv("GPCC_LARGE_NO_LOOKAHEAD"));
     bool bulk_pending[2] = {false, false};
-    for (int k = 0; k < T; ++k) {
+    for (int k = 0; k < ksteps; ++k) {
         pivot_kernel<<<nb, 256, pivot_smem, st>>>(a, k);
         ++launches;
         const int I0 = a.sweep ? 0 : k + 1;
@@ -1005,6 +1135,7 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, in
         gather_kernel<<<dim3(nI, nb), 256, 0, st>>>(a, k, I0);
         panel_kernel<<<dim3(nI, nb, a.sweep ? 2 : 1), 256, gemm_smem, st>>>(a, k, I0);
         launches += 2;
+        if (a.cmode == 1) { export_x_kernel<<<dim3(T - Tc, nb), 256, 0, st>>>(a, k); ++launches; }
         const bool has_next = (k + 1 < T);
         const int n_crit = a.sweep ? T - 1 : T - 1 - k;                 // tiles of block row/column k+1
         const int n_rest_side = a.sweep ? T - 2 : T - 2 - k;
@@ -1031,12 +1162,16 @@ cudaError_t run_wave(const DevProblem& p, const EvalBatch& b, int e0, int nb, in
     for (int q = 0; q < 2; ++q)
         if (bulk_pending[q]) cudaStreamWaitEvent(st, w.ev_bulk[q], 0);
     if (profile) cudaEventRecord(w.ev[2], st);
+    if (a.cmode == 1) {
+        const int nC = T - Tc;
+        export_state_kernel<<<dim3(nC * (nC + 1) / 2 + 1, nb), 256, 0, st>>>(a);
+        ++launches;
+    }
     if (b.want_grad) {
         gradreduce_kernel<KID><<<dim3(ntiles, nb), 256, 0, st>>>(b, e0, a);
         ++launches;
     }
-    finalize_kernel<<<nb, 256, 0, st>>>(p, b, e0, a);
-    ++launches;
+    if (a.cmode != 1) { finalize_kernel<<<nb, 256, 0, st>>>(p, b, e0, a); ++launches; }
     if (b.dump_chol && !a.sweep) {
         dump_chol_kernel<<<dim3(592, nb), 256, 0, st>>>(b, e0, a);
         ++launches;
@@ -1090,6 +1225,57 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
         rl.assign(b.M, 1);
         for (int x = b.M - 2; x >= 0; --x) if (same_prefix(x, x + 1)) rl[x] = rl[x + 1] + 1;
     }
+    // Last-band cache (three bands, boundaries on tile boundaries, one theta and one first delay for the whole batch -- the
+    // fixed-theta grid sweep): what the band-1 steps do to the rows of band 3 depends on tau_3 alone.  A grid has far fewer
+    // distinct tau_3 than candidates, so those steps run once per distinct value (FILL waves) and every candidate imports
+    // their result (USE): per candidate 4.3 n^3 + the amortised fill instead of 6.3 n^3 flop (n = points per band), bitwise the
+    // same tiles as without the cache (same kernels, same operands, same order).
+    static const bool no_cache = getenv("GPCC_LARGE_NO_TAUCACHE") != nullptr;
+    bool use_cache = false;
+    int Tq = 0, Tc = 0, nslots = 0;
+    std::vector<int> slot_of, rep;
+    if (Tp_full > 0 && L == 3 && !no_cache && !b.dump_chol && !b.mode_postb && p.band_start[1] >= BT && p.band_start[1] % BT == 0 &&
+        p.band_start[2] % BT == 0 && b.M >= 8) {
+        bool same = true;
+        for (int x = 1; x < b.M && same; ++x) {
+            same = memcmp(&b.h_rho[x], &b.h_rho[0], sizeof(double)) == 0 &&
+                   memcmp(&b.h_alpha[(size_t)x * L], &b.h_alpha[0], L * sizeof(double)) == 0 &&
+                   memcmp(&b.h_delays[(size_t)x * L], &b.h_delays[0], sizeof(double)) == 0;
+        }
+        if (same) {
+            std::map<uint64_t, int> ids;
+            slot_of.resize(b.M);
+            for (int x = 0; x < b.M; ++x) {
+                uint64_t bits;
+                memcpy(&bits, &b.h_delays[(size_t)x * L + L - 1], sizeof(bits));
+                auto it = ids.find(bits);
+                if (it == ids.end()) { it = ids.emplace(bits, (int)rep.size()).first; rep.push_back(x); }
+                slot_of[x] = it->second;
+            }
+            nslots = (int)rep.size();
+            Tq = p.band_start[1] / BT; Tc = p.band_start[2] / BT;
+            // worth it when a slot serves several candidates (the fill of a slot costs about a third of a candidate)
+            if (b.M >= 3 * nslots && Tc < w.T && ensure_cache(w, nslots, Tq, Tc)) use_cache = true;
+        }
+    }
+    auto dispatch = [&](int e0, int nb, int Tp, int cmode, const int* h_eidx, const int* h_slot) {
+        switch (p.kernel_id) {
+            case K_OU:  return run_wave<K_OU>(p, b, e0, nb, Tp, w, stream, profile, tm, cmode, Tq, Tc, h_eidx, h_slot);
+            case K_RBF: return run_wave<K_RBF>(p, b, e0, nb, Tp, w, stream, profile, tm, cmode, Tq, Tc, h_eidx, h_slot);
+            case K_M32: return run_wave<K_M32>(p, b, e0, nb, Tp, w, stream, profile, tm, cmode, Tq, Tc, h_eidx, h_slot);
+            default:    return run_wave<K_M52>(p, b, e0, nb, Tp, w, stream, profile, tm, cmode, Tq, Tc, h_eidx, h_slot);
+        }
+    };
+    if (use_cache) {
+        std::vector<int> ids(w.B);
+        for (int s0 = 0; s0 < nslots; s0 += w.B) {
+            const int nb = std::min(w.B, nslots - s0);
+            for (int m = 0; m < nb; ++m) ids[m] = s0 + m;
+            e = dispatch(0, nb, 0, 1, rep.data() + s0, ids.data());
+            if (e != cudaSuccess) return e;
+        }
+        tm->tau_cache_evals += b.M;
+    }
     constexpr int MIN_RUN = 4;
     for (int e0 = 0; e0 < b.M;) {
         int nb = 0, Tp = 0;
@@ -1101,12 +1287,7 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
         } else {                                             // no sharing: up to a full wave, but stop where a long run begins
             while (nb < w.B && e0 + nb < b.M && !(nb > 0 && Tp_full > 0 && rl[e0 + nb] >= MIN_RUN)) ++nb;
         }
-        switch (p.kernel_id) {
-            case K_OU:  e = run_wave<K_OU>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
-            case K_RBF: e = run_wave<K_RBF>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
-            case K_M32: e = run_wave<K_M32>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
-            default:    e = run_wave<K_M52>(p, b, e0, nb, Tp, w, stream, profile, tm); break;
-        }
+        e = dispatch(e0, nb, Tp, use_cache ? 2 : 0, nullptr, use_cache ? slot_of.data() + e0 : nullptr);
         if (e != cudaSuccess) return e;
         e0 += nb;
     }

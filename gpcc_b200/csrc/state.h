@@ -75,7 +75,7 @@ struct DeviceState {
     LargeWorkspace large;     // tiled large-N path (large_path.cu)
     // per-call statistics (profiling)
     double ms_eval = 0, ms_assembly = 0, ms_factor = 0, ms_gradreduce = 0;
-    long long launches = 0, evals = 0, evals_grad = 0, shared_prefix_evals = 0;
+    long long launches = 0, evals = 0, evals_grad = 0, shared_prefix_evals = 0, tau_cache_evals = 0, assembly_bytes = 0;
 };
 
 }  // namespace gpcc

@@ -315,6 +315,56 @@ def test_large_path_matches_oracle(ctx, nper, kernel):
     assert np.array_equal(again[0], ll) and np.array_equal(again[1], grad)      # deterministic
 
 
+def test_last_band_cache(ctx):
+    """Fixed-theta sweep over three bands whose boundaries fall on tile boundaries: what the band-1 pivots do to the rows of band 3
+    depends on tau_3 alone (block (3,1) of the covariance: src/delayedCovariance.jl:23-31), so it is computed once per distinct
+    tau_3 and imported by every candidate (large_path.cu, last-band cache).  Same kernels on the same operands in the same
+    order: the log-likelihoods are BITWISE those of a run without the cache; oracle parity as everywhere."""
+    import os, subprocess, sys, tempfile
+    nper = [256, 256, 200]                                                             # N = 712: T = 6 tiles, Tq = 2, Tc = 4
+    t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=21)
+    p = Problem(t, y, s, "matern52", ctx)
+    c2, c3 = np.arange(0.0, 2.51, 0.5), np.arange(0.0, 7.01, 1.0)
+    delays = np.array([[0.0, a, b] for b in c3 for a in c2])                          # 48 candidates, 8 distinct tau_3
+    M = len(delays)
+    alpha, rho = np.tile([0.9, 1.7, 2.2], (M, 1)), np.full(M, 3.1)
+    ll, info = p.loglik_batch(delays, alpha, rho)
+    st = ctx.stats()
+    assert st["path"] == 1 and np.all(info == 0) and st["n_tau_cache"] == M and st["n_shared_prefix"] > 0
+    op = oracle.Problem(t, y, s, "matern52")
+    for m in (0, 5, 29, M - 1):
+        assert abs(ll[m] - op.loglik(delays[m], alpha[m], rho[m])) / abs(ll[m]) < LL_RTOL
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\nimport gpcc_b200\n"
+            "t, y, s, d = gpcc_b200.synthetic_bands([256, 256, 200], seed=21)\n"
+            "p = gpcc_b200.Problem(t, y, s, 'matern52')\n"
+            "z = np.load(sys.argv[1]); ll, info = p.loglik_batch(z['delays'], z['alpha'], z['rho'])\n"
+            "assert gpcc_b200.default_context().stats()['n_tau_cache'] == 0\n"
+            "np.save(sys.argv[2], ll)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(os.path.join(tmp, "in.npz"), delays=delays, alpha=alpha, rho=rho)
+        r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, "in.npz"), os.path.join(tmp, "out.npy")],
+                           env=dict(os.environ, GPCC_LARGE_NO_TAUCACHE="1"), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        ll_plain = np.load(os.path.join(tmp, "out.npy"))
+    assert np.array_equal(ll, ll_plain)
+    for _ in range(3):                                                                 # deterministic (no race between the waves)
+        assert np.array_equal(p.loglik_batch(delays, alpha, rho)[0], ll)
+    perm = np.random.default_rng(5).permutation(M)                                     # any order of the candidates: another
+    ll_p, _ = p.loglik_batch(delays[perm], alpha[perm], rho[perm])                     # candidate leads each wave (it sums
+    assert np.max(np.abs(ll_p - ll[perm]) / np.abs(ll)) < 1e-14                        # log-det and quadratic form in one go)
+    # mixed hyper-parameters: no cache, same numbers for the untouched candidates
+    alpha2 = alpha.copy(); alpha2[7, 1] = 1.9
+    ll2, _ = p.loglik_batch(delays, alpha2, rho)
+    assert ctx.stats()["n_tau_cache"] == 0 and np.max(np.abs(np.delete(ll2, 7) - np.delete(ll, 7)) / np.abs(np.delete(ll, 7))) < 1e-14
+    # a second sweep with other hyper-parameters refills the cache (entries belong to one call)
+    ll3, _ = p.loglik_batch(delays, alpha * 1.25, rho * 0.8)
+    assert abs(ll3[11] - op.loglik(delays[11], alpha[11] * 1.25, rho[11] * 0.8)) / abs(ll3[11]) < LL_RTOL
+    # the grid driver with iterations = 0 takes the same route
+    th = np.concatenate([np.log(np.expm1(np.array([0.9, 1.7, 2.2]))), [np.log((3.1 - 0.1) / (300.0 - 3.1))]])[None]
+    r = p.grid_posterior(delays, th, iterations=0, rhomin=0.1, rhomax=300.0)
+    assert ctx.stats()["n_tau_cache"] == M and abs(r["posterior"].sum() - 1.0) < 1e-12
+
+
 def test_structure_reuse_across_the_grid(ctx):
     """Fixed-theta sweep on the tiled path: candidates that share the hyper-parameters and the delays of all
     bands but the last share the leading block of the covariance (src/delayedCovariance.jl:23-31); a wave factorises it once.
