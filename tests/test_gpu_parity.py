@@ -356,6 +356,19 @@ def test_last_band_cache(ctx):
     alpha2 = alpha.copy(); alpha2[7, 1] = 1.9
     ll2, _ = p.loglik_batch(delays, alpha2, rho)
     assert ctx.stats()["n_tau_cache"] == 0 and np.max(np.abs(np.delete(ll2, 7) - np.delete(ll, 7)) / np.abs(np.delete(ll, 7))) < 1e-14
+    # many tau_2, few tau_3: the runs with a common tau_2 are too short to share their leading block (every matrix factorises
+    # its own bands 1-2), the last-band cache serves them all the same
+    c2b = np.arange(0.0, 3.76, 0.25)
+    delays_b = np.array([[0.0, a, b] for a in c2b for b in c3[:3]])
+    Mb = len(delays_b)
+    ll_b, info_b = p.loglik_batch(delays_b, np.tile(alpha[0], (Mb, 1)), np.full(Mb, rho[0]))
+    st_b = ctx.stats()
+    assert np.all(info_b == 0) and st_b["n_tau_cache"] == Mb and st_b["n_shared_prefix"] == 0
+    for m in range(Mb):
+        hit = np.where(np.all(delays == delays_b[m], axis=1))[0]
+        if len(hit):
+            assert abs(ll_b[m] - ll[hit[0]]) / abs(ll_b[m]) < 1e-14
+    assert abs(ll_b[4] - op.loglik(delays_b[4], alpha[0], rho[0])) / abs(ll_b[4]) < LL_RTOL
     # a second sweep with other hyper-parameters refills the cache (entries belong to one call)
     ll3, _ = p.loglik_batch(delays, alpha * 1.25, rho * 0.8)
     assert abs(ll3[11] - op.loglik(delays[11], alpha[11] * 1.25, rho[11] * 0.8)) / abs(ll3[11]) < LL_RTOL
