@@ -315,14 +315,14 @@ def test_large_path_matches_oracle(ctx, nper, kernel):
     assert np.array_equal(again[0], ll) and np.array_equal(again[1], grad)      # deterministic
 
 
-def test_last_band_cache(ctx):
-    """Fixed-theta sweep over three bands whose boundaries fall on tile boundaries: what the band-1 pivots do to the rows of band 3
+@pytest.mark.parametrize("nper", [[256, 256, 200], [300, 280, 330]])   # boundaries on / off the 128-wide tile boundaries
+def test_last_band_cache(ctx, nper):
+    """Fixed-theta sweep over three bands: what the band-1 pivots do to the rows of band 3
     depends on tau_3 alone (block (3,1) of the covariance: src/delayedCovariance.jl:23-31), so it is computed once per distinct
     tau_3 and imported by every candidate (large_path.cu, last-band cache).  Same kernels on the same operands in the same
     order: the log-likelihoods are BITWISE those of a run without the cache; oracle parity as everywhere."""
     import os, subprocess, sys, tempfile
-    nper = [256, 256, 200]                                                             # N = 712: T = 6 tiles, Tq = 2, Tc = 4
-    t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=21)
+    t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=21)                              # N = 712: T = 6 tiles, Tq = 2, Tc = 4 / N = 910: T = 8, 2, 5
     p = Problem(t, y, s, "matern52", ctx)
     c2, c3 = np.arange(0.0, 2.51, 0.5), np.arange(0.0, 7.01, 1.0)
     delays = np.array([[0.0, a, b] for b in c3 for a in c2])                          # 48 candidates, 8 distinct tau_3
@@ -335,11 +335,11 @@ def test_last_band_cache(ctx):
     for m in (0, 5, 29, M - 1):
         assert abs(ll[m] - op.loglik(delays[m], alpha[m], rho[m])) / abs(ll[m]) < LL_RTOL
     code = ("import numpy as np, sys; sys.path.insert(0, %r)\nimport gpcc_b200\n"
-            "t, y, s, d = gpcc_b200.synthetic_bands([256, 256, 200], seed=21)\n"
+            "t, y, s, d = gpcc_b200.synthetic_bands(%r, seed=21)\n"
             "p = gpcc_b200.Problem(t, y, s, 'matern52')\n"
             "z = np.load(sys.argv[1]); ll, info = p.loglik_batch(z['delays'], z['alpha'], z['rho'])\n"
             "assert gpcc_b200.default_context().stats()['n_tau_cache'] == 0\n"
-            "np.save(sys.argv[2], ll)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            "np.save(sys.argv[2], ll)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), nper)
     with tempfile.TemporaryDirectory() as tmp:
         np.savez(os.path.join(tmp, "in.npz"), delays=delays, alpha=alpha, rho=rho)
         r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, "in.npz"), os.path.join(tmp, "out.npy")],
@@ -575,6 +575,12 @@ def test_cfg4_sizes_match_oracle_fixture(ctx, tag):
     assert np.max(np.abs(ll_f - g[tag + "_ll"]) / np.abs(g[tag + "_ll"])) < LL_RTOL
     assert np.max(np.abs(ll_s - g[tag + "_ll"]) / np.abs(g[tag + "_ll"])) < LL_RTOL
     assert np.max(np.abs(grad - g[tag + "_grad"]) / np.max(np.abs(g[tag + "_grad"]), axis=1, keepdims=True)) < GRAD_RTOL
+    # the same candidate inside a fixed-theta sweep (3 tau_2 x 4 tau_3): shared leading block + last-band cache, same 1e-10
+    sweep = np.array([[0.0, a, b] for a in (delays[0, 1], 2.4, 2.8) for b in (delays[0, 2], 4.6, 5.2, 5.8)])
+    ll_w, info_w = p.loglik_batch(sweep, np.tile(alpha[0], (len(sweep), 1)), np.full(len(sweep), rho[0]))
+    st = ctx.stats()
+    assert np.all(info_w == 0) and st["n_tau_cache"] == len(sweep) and st["n_shared_prefix"] > 0
+    assert abs(ll_w[0] - g[tag + "_ll"][0]) / abs(g[tag + "_ll"][0]) < LL_RTOL and abs(ll_w[0] - ll_f[0]) / abs(ll_f[0]) < 1e-14
 
 
 def test_cfg4_size_properties(ctx):
