@@ -390,7 +390,7 @@ def main():
             sel4 = np.array([m for m in range(len(grid4)) if m % 8 < min(world, 8)])
             d4 = grid4[sel4][: share * world]
             th4 = np.concatenate([np.log(np.expm1(np.array([1.0, 2.2, 4.0]))), [np.log((3.5 - RHOMIN) / (RHOMAX - 3.5))]])[None]
-            p4.grid_posterior(d4[: 16 * world], th4, iterations=0, rhomin=RHOMIN, rhomax=RHOMAX)            # warm-up (workspace allocation)
+            p4.grid_posterior(d4[: 40 * world], th4, iterations=0, rhomin=RHOMIN, rhomax=RHOMAX)            # warm-up: a full wave of 32 matrices per rank, so that the workspace and the last-band cache have their final size (a 16-candidate warm-up left a 5 GB re-allocation, 0.1-0.7 s, inside the timed call)
             barrier()
             t0 = time.perf_counter()
             r4 = p4.grid_posterior(d4, th4, iterations=0, rhomin=RHOMIN, rhomax=RHOMAX)

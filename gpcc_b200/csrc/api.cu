@@ -524,7 +524,7 @@ int fit_all(gpcc_problem* p, int M, const double* delays, int P, const double* t
 // =====================================================================================================
 extern "C" {
 
-int gpcc_version(void) { return 100; }
+int gpcc_version(void) { return 101; }   // 101: gpcc_stats grew by n_tau_cache and assembly_bytes (appended)
 const char* gpcc_last_error(void) { return gpcc::last_error().c_str(); }
 
 int gpcc_fit_options_default(gpcc_fit_options* o) {

@@ -79,7 +79,8 @@ typedef struct gpcc_stats {
                                    tiles imported from the last-band cache count read + written); pairs with ms_assembly      */
 } gpcc_stats;
 
-int         gpcc_version(void);
+int         gpcc_version(void);   /* 101.  100 -> 101: gpcc_stats grew by n_tau_cache and assembly_bytes (appended at the end);
+                                      a caller built against 100 must be rebuilt before it calls gpcc_ctx_get_stats                */
 const char* gpcc_last_error(void);
 
 /* CUDA contexts, streams, workspaces on `ndev` devices (dev_ids NULL = 0..ndev-1).  With ndev>1 the

@@ -16,7 +16,7 @@ c4 = np.arange(0.0, 19.8001, 0.2)
 grid4 = np.array([[0.0, a, b] for b in c4 for a in c4])
 d4 = grid4[np.arange(0, len(grid4), 8)][:n]
 th4 = np.concatenate([np.log(np.expm1(np.array([1.0, 2.2, 4.0]))), [np.log((3.5 - 0.1) / (300.0 - 3.5))]])[None]
-p4.grid_posterior(d4[:16], th4, iterations=0, rhomin=0.1, rhomax=300.0)
+p4.grid_posterior(d4[:40], th4, iterations=0, rhomin=0.1, rhomax=300.0)
 t0 = time.perf_counter()
 r = p4.grid_posterior(d4, th4, iterations=0, rhomin=0.1, rhomax=300.0)
 dt = time.perf_counter() - t0
