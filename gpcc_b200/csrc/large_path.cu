@@ -71,7 +71,7 @@ struct LargeArgs {
     double* epart;      // [B][ntiles]
     size_t mat_stride;  // doubles per matrix
     size_t x_parity_stride;   // Xws is double buffered by step parity (look-ahead: update k still reads X_k while panel k+1 writes)
-    // Last-band cache (forward mode, three bands; see large_eval).  Pivots k < Tq lie in band 1,
+    // Last-band cache (forward mode, three or more bands; see large_eval).  Pivots k < Tq lie in band 1,
     // block rows I >= Tc in the last band.  What steps k < Tq do to the last band's rows -- the panels X_I^(k), the state of block
     // (3,3) and of r_3 after step Tq-1 -- depends on the LAST delay only: cmode 1 (FILL) computes it once per distinct value and
     // exports it to slot[m]; cmode 2 (USE) imports it instead of recomputing it for every candidate.
@@ -1225,8 +1225,8 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
         rl.assign(b.M, 1);
         for (int x = b.M - 2; x >= 0; --x) if (same_prefix(x, x + 1)) rl[x] = rl[x + 1] + 1;
     }
-    // Last-band cache (three bands, one theta and one first delay for the whole batch -- the fixed-theta grid sweep): what the
-    // band-1 steps do to the rows of band 3 depends on tau_3 alone.  A grid has far fewer
+    // Last-band cache (three or more bands, one theta and one first delay for the whole batch -- the fixed-theta grid sweep): what
+    // the band-1 steps do to the rows of the last band depends on the last delay alone (written for three bands below).  A grid has far fewer
     // distinct tau_3 than candidates, so those steps run once per distinct value (FILL waves) and every candidate imports
     // their result (USE): per candidate 4.3 n^3 + the amortised fill instead of 6.3 n^3 flop (n = points per band), bitwise the
     // same tiles as without the cache (same kernels, same operands, same order).
@@ -1234,7 +1234,7 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
     bool use_cache = false;
     int Tq = 0, Tc = 0, nslots = 0;
     std::vector<int> slot_of, rep;
-    if (Tp_full > 0 && L == 3 && !no_cache && !b.dump_chol && !b.mode_postb && p.band_start[1] >= BT && b.M >= 8) {
+    if (Tp_full > 0 && L >= 3 && !no_cache && !b.dump_chol && !b.mode_postb && p.band_start[1] >= BT && b.M >= 8) {
         bool same = true;
         for (int x = 1; x < b.M && same; ++x) {
             same = memcmp(&b.h_rho[x], &b.h_rho[0], sizeof(double)) == 0 &&
@@ -1253,8 +1253,8 @@ cudaError_t large_eval(const DevProblem& p, const EvalBatch& b, LargeWorkspace& 
             }
             nslots = (int)rep.size();
             Tq = p.band_start[1] / BT;                   // block columns entirely inside band 1
-            Tc = (p.band_start[2] + BT - 1) / BT;        // block rows entirely inside band 3 (a row of tiles that straddles the
-                                                         // boundary is handled like band 2: per candidate)
+            Tc = (p.band_start[L - 1] + BT - 1) / BT;    // block rows entirely inside the last band (a row of tiles that straddles
+                                                         // its boundary is handled like the middle bands: per candidate)
             // worth it when a slot serves several candidates (the fill of a slot costs about a third of a candidate)
             if (b.M >= 3 * nslots && Tc < w.T && ensure_cache(w, nslots, Tq, Tc)) use_cache = true;
         }

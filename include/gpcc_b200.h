@@ -73,7 +73,7 @@ typedef struct gpcc_stats {
     int    n_devices;
     long long n_shared_prefix;  /* tiled path, logL only: evaluations whose leading block (all bands but the
                                    last) was factorised by another evaluation of their wave (structure reuse) */
-    long long n_tau_cache;      /* tiled path, fixed-theta sweep over three bands: evaluations that took the band-1 steps of
+    long long n_tau_cache;      /* tiled path, fixed-theta sweep over >= 3 bands: evaluations that took the band-1 steps of
                                    their last band (a function of the last delay alone) from the last-band cache            */
     long long assembly_bytes;   /* tiled path: HBM bytes the assembly kernels of the busiest device moved (tiles written;
                                    tiles imported from the last-band cache count read + written); pairs with ms_assembly      */

@@ -1,4 +1,4 @@
-"""Randomised A/B of the last-band cache of the tiled path: for a few three-band problems (band boundaries on and off the tile
+"""Randomised A/B of the last-band cache of the tiled path: for a few three- and four-band problems (band boundaries on and off the tile
 boundaries) and candidate sets (full grids, random subsets, repeated candidates) the log-likelihoods with the cache must be
 BITWISE those of a process started with GPCC_LARGE_NO_TAUCACHE=1.  Usage: check_last_band_cache.py   (parent)"""
 import os, subprocess, sys, tempfile
@@ -6,11 +6,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = [([128, 128, 128], "matern32"), ([130, 200, 140], "OU"), ([400, 100, 300], "rbf"), ([1000, 700, 900], "matern52"), ([256, 512, 384], "matern32")]
+CASES = [([128, 128, 128], "matern32"), ([130, 200, 140], "OU"), ([400, 100, 300], "rbf"), ([1000, 700, 900], "matern52"), ([256, 512, 384], "matern32"), ([300, 128, 200, 260], "matern52")]
 
-def candidates(rg, case):
+def candidates(rg, case, L):
     c2, c3 = np.sort(rg.uniform(0, 8, rg.integers(2, 7))), np.sort(rg.uniform(0, 8, rg.integers(2, 9)))
-    grid = np.array([[0.0, a, b] for b in c3 for a in c2])
+    grid = np.array([[0.0] + [2.1] * (L - 3) + [a, b] for b in c3 for a in c2])
     kind = case % 3
     if kind == 1: grid = grid[rg.permutation(len(grid))[: max(8, 2 * len(grid) // 3)]]
     if kind == 2: grid = np.concatenate([grid, grid[rg.integers(0, len(grid), 5)]])
@@ -25,9 +25,9 @@ def run(tag):
         t, y, s, _ = gpcc_b200.synthetic_bands(nper, seed=30 + ci)
         p = gpcc_b200.Problem(t, y, s, kernel, ctx)
         for rep in range(3):
-            d = candidates(rg, ci + rep)
+            d = candidates(rg, ci + rep, len(nper))
             M = len(d)
-            alpha, rho = np.tile(rg.uniform(0.5, 2.5, 3), (M, 1)), np.full(M, rg.uniform(1.0, 6.0))
+            alpha, rho = np.tile(rg.uniform(0.5, 2.5, len(nper)), (M, 1)), np.full(M, rg.uniform(1.0, 6.0))
             ll, info = p.loglik_batch(d, alpha, rho)
             st = ctx.stats()
             out["ll_%d_%d" % (ci, rep)] = ll

@@ -315,7 +315,7 @@ def test_large_path_matches_oracle(ctx, nper, kernel):
     assert np.array_equal(again[0], ll) and np.array_equal(again[1], grad)      # deterministic
 
 
-@pytest.mark.parametrize("nper", [[256, 256, 200], [300, 280, 330]])   # boundaries on / off the 128-wide tile boundaries
+@pytest.mark.parametrize("nper", [[256, 256, 200], [300, 280, 330], [200, 150, 180, 220]])   # boundaries on / off the 128-wide tile boundaries; four bands
 def test_last_band_cache(ctx, nper):
     """Fixed-theta sweep over three bands: what the band-1 pivots do to the rows of band 3
     depends on tau_3 alone (block (3,1) of the covariance: src/delayedCovariance.jl:23-31), so it is computed once per distinct
@@ -325,9 +325,12 @@ def test_last_band_cache(ctx, nper):
     t, y, s, d = gpcc_b200.synthetic_bands(nper, seed=21)                              # N = 712: T = 6 tiles, Tq = 2, Tc = 4 / N = 910: T = 8, 2, 5
     p = Problem(t, y, s, "matern52", ctx)
     c2, c3 = np.arange(0.0, 2.51, 0.5), np.arange(0.0, 7.01, 1.0)
-    delays = np.array([[0.0, a, b] for b in c3 for a in c2])                          # 48 candidates, 8 distinct tau_3
+    L = len(nper)
+    mk = lambda a, b: [0.0] + [1.3] * (L - 3) + [a, b]                                 # the grid runs over the last two delays
+    a0 = np.array([0.9, 1.7, 2.2, 1.4])[:L]
+    delays = np.array([mk(a, b) for b in c3 for a in c2])                             # 48 candidates, 8 distinct last delays
     M = len(delays)
-    alpha, rho = np.tile([0.9, 1.7, 2.2], (M, 1)), np.full(M, 3.1)
+    alpha, rho = np.tile(a0, (M, 1)), np.full(M, 3.1)
     ll, info = p.loglik_batch(delays, alpha, rho)
     st = ctx.stats()
     assert st["path"] == 1 and np.all(info == 0) and st["n_tau_cache"] == M and st["n_shared_prefix"] > 0
@@ -359,7 +362,7 @@ def test_last_band_cache(ctx, nper):
     # many tau_2, few tau_3: the runs with a common tau_2 are too short to share their leading block (every matrix factorises
     # its own bands 1-2), the last-band cache serves them all the same
     c2b = np.arange(0.0, 3.76, 0.25)
-    delays_b = np.array([[0.0, a, b] for a in c2b for b in c3[:3]])
+    delays_b = np.array([mk(a, b) for a in c2b for b in c3[:3]])
     Mb = len(delays_b)
     ll_b, info_b = p.loglik_batch(delays_b, np.tile(alpha[0], (Mb, 1)), np.full(Mb, rho[0]))
     st_b = ctx.stats()
@@ -373,7 +376,7 @@ def test_last_band_cache(ctx, nper):
     ll3, _ = p.loglik_batch(delays, alpha * 1.25, rho * 0.8)
     assert abs(ll3[11] - op.loglik(delays[11], alpha[11] * 1.25, rho[11] * 0.8)) / abs(ll3[11]) < LL_RTOL
     # the grid driver with iterations = 0 takes the same route
-    th = np.concatenate([np.log(np.expm1(np.array([0.9, 1.7, 2.2]))), [np.log((3.1 - 0.1) / (300.0 - 3.1))]])[None]
+    th = np.concatenate([np.log(np.expm1(a0)), [np.log((3.1 - 0.1) / (300.0 - 3.1))]])[None]
     r = p.grid_posterior(delays, th, iterations=0, rhomin=0.1, rhomax=300.0)
     assert ctx.stats()["n_tau_cache"] == M and abs(r["posterior"].sum() - 1.0) < 1e-12
 
