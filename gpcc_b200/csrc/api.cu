@@ -315,7 +315,7 @@ int fit_shard(gpcc_problem* p, int di, const std::vector<int>& idx, const double
     DeviceState& s = p->ctx->ds[di];
     EvalSlot& q0 = s.slot[0];
     LbfgsOptions lo;
-    lo.max_iter = o.max_iter; lo.gtol = o.gtol; lo.ftol = o.ftol; lo.history = o.history;
+    lo.max_iter = o.max_iter; lo.gtol = o.gtol; lo.ftol = o.ftol; lo.history = o.history; lo.n_scale = L;
     static const double dec_env = getenv("GPCC_LBFGS_DEC") ? atof(getenv("GPCC_LBFGS_DEC")) : 0.0;   // experiment switch
     lo.dec_tol = dec_env;
 

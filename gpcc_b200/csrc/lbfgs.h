@@ -32,6 +32,8 @@ struct LbfgsOptions {
     int history = 8;
     int max_ls = 30;
     double dec_tol = 0.0;   // > 0: stop when the quasi-Newton estimate of the remaining decrease, 0.5 g'Hg, is below it
+    int n_scale = 0;        // the first n_scale coordinates are softplus scales (alpha): their step cap grows with the coordinate
+    double rel_cap = 0.25;  // ... to rel_cap * theta_i once that exceeds STEP_CAP
 };
 
 struct LbfgsState {
@@ -48,6 +50,8 @@ struct LbfgsState {
     double S[LBFGS_MAXM][LBFGS_MAXN], Y[LBFGS_MAXM][LBFGS_MAXN], R[LBFGS_MAXM];
     int hcount = 0, hhead = 0;         // ring buffer
     int small_df = 0;
+    int n_scale = 0;                   // copies of the options new_direction needs
+    double rel_cap = 0.0;
 
     GPCC_HD static double dot(const double* a, const double* b, int n) {
         double s = 0.0;
@@ -64,6 +68,8 @@ struct LbfgsState {
         iters = 0;
         hcount = hhead = 0;
         small_df = 0;
+        n_scale = o.n_scale;
+        rel_cap = o.rel_cap;
         double gmax = 0.0;
         for (int i = 0; i < n; ++i) gmax = fmax(gmax, fabs(g[i]));
         if (!(gmax > o.gtol)) { status = CONVERGED; return; }
@@ -106,9 +112,18 @@ struct LbfgsState {
         // Cap the step at STEP_CAP units of the unconstrained parameters per iteration.  theta lives on the softplus /
         // logistic scale: a jump of many units lands where the transforms saturate (alpha -> floor, rho -> rhomin), their
         // Jacobians vanish and a gradient method crawls for hundreds of iterations in a degenerate basin.
-        double dmax = 0.0;
-        for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(d[i]));
-        tcap = dmax > 0.0 ? STEP_CAP / dmax : lb_inf();
+        // A scale far up the linear branch of the softplus (theta_i = alpha_i >> 1) is nowhere near saturation, and a fixed cap
+        // makes the optimiser walk: the candidates at the edge of the grid, where the last band hardly overlaps the others,
+        // have their optimum at alpha ~ 150 and needed 75 capped iterations to get there (the 170-220-evaluation tail of the
+        // fitted grid).  For those coordinates the cap is rel_cap * theta_i once that exceeds STEP_CAP: geometric instead of
+        // linear travel.  The rho coordinate (logistic) and everything at or below the knee keep the fixed cap.
+        tcap = lb_inf();
+        for (int i = 0; i < n; ++i) {
+            const double ad = fabs(d[i]);
+            if (!(ad > 0.0)) continue;
+            const double cap = (i < n_scale) ? fmax(STEP_CAP, rel_cap * x[i]) : STEP_CAP;
+            tcap = fmin(tcap, cap / ad);
+        }
         t = fmin(t, tcap);
         tlo = 0.0;
         thi = lb_inf();

@@ -153,7 +153,7 @@ small_fit_kernel(DevProblem p, FitParams fp, FitBuffers fb, int T, int ctl_offse
     FitCtl& c = *reinterpret_cast<FitCtl*>(smem + ctl_offset_doubles);
     const int tid = threadIdx.x, L = p.L, n = L + 1;
     LbfgsOptions lo;
-    lo.max_iter = fp.max_iter; lo.gtol = fp.gtol; lo.ftol = fp.ftol; lo.history = fp.history;
+    lo.max_iter = fp.max_iter; lo.gtol = fp.gtol; lo.ftol = fp.ftol; lo.history = fp.history; lo.n_scale = L;
     if (tid == 0) {                                        // schedule diagnostics: when did the first CTA start
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
