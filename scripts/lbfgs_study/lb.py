@@ -1,4 +1,5 @@
-# Python port of gpcc_b200/csrc/lbfgs.h for an evaluation-count study on the oracle objective (CPU)
+# Python port of gpcc_b200/csrc/lbfgs.h for evaluation-count studies on the oracle objective (CPU).  variant=None is the state machine as it
+# was before the relative step cap; variant={"relcap": 0.25} is the rule lbfgs.h ships now (n_scale = L, rel_cap = 0.25).
 import numpy as np, sys, time
 import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
 from oracle.model import Problem
